@@ -1,0 +1,134 @@
+/* potus_b200.h -- C-ABI of the B200-native NUTS sampler for The Economist's poll model.
+ *
+ * This is the drop-in boundary for the ONE hot path of TheEconomist/us-potus-model: everything
+ * that happens between the R drivers handing the named `data` list to Stan and getting draws back
+ *   scripts/model/final_2016.R:532-543   cmdstan_model(...)$sample(data=, seed=, chains=, ...) ;
+ *                                        rstan::read_stan_csv(fit$output_files())
+ *   scripts/model/final_2012.R:558-569, scripts/model/final_2008.R:562-573   (same call)
+ * i.e. the log-posterior + gradient of scripts/model/poll_model_2020.stan (and the
+ * _no_mode_adjustment variant), leapfrog, multinomial NUTS, Stan's warm-up adaptation, and the
+ * transformed parameters / generated quantities the R consumers extract
+ * (final_2016.R:556,568,597,622,647,682,708; README.Rmd:206,716,1240).
+ *
+ * Plain C: pointers and sizes only.  All indices in PotusData are 1-BASED exactly as R/Stan hold
+ * them (poll_model_2020.stan:9-17).  No C++ exception or CUDA error crosses this boundary: every
+ * entry point returns POTUS_OK or a negative status and leaves a message for potus_last_error().
+ * The reference-side binding (R .Call shim) is r/potus_b200_rshim.c; see INTEGRATION.md.
+ */
+#ifndef POTUS_B200_H
+#define POTUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POTUS_OK 0
+#define POTUS_ERR_INVALID_DATA (-1)   /* Stan data-block constraint violated (poll_model_2020.stan:9-23,37) */
+#define POTUS_ERR_UNSUPPORTED (-2)    /* problem size outside what the resident kernel handles */
+#define POTUS_ERR_CUDA (-3)           /* CUDA runtime / driver error, or no sm_100 device */
+#define POTUS_ERR_STATE (-4)          /* call order (e.g. get_draws before run) or unknown name */
+#define POTUS_ERR_INIT (-5)           /* no finite initial point after 100 attempts (Stan's rule) */
+
+/* The named list of final_2016.R:475-514 (2012/2008: final_2012.R:501-540, final_2008.R:504-545;
+ * their extra names sigma_a/M/Pop/unadjusted_* are accepted and ignored by the binding).
+ * poll_mode_* / poll_pop_* == NULL selects poll_model_2020_no_mode_adjustment.stan. */
+typedef struct PotusData {
+  int32_t N_national_polls, N_state_polls, T, S, P, M, Pop;
+  const int32_t* state;              /* [N_state_polls]    1..S              */
+  const int32_t* day_state;          /* [N_state_polls]    1..T              */
+  const int32_t* day_national;       /* [N_national_polls] 1..T              */
+  const int32_t* poll_state;         /* [N_state_polls]    1..P              */
+  const int32_t* poll_national;      /* [N_national_polls] 1..P              */
+  const int32_t* poll_mode_state;    /* [N_state_polls]    1..M   or NULL    */
+  const int32_t* poll_mode_national; /* [N_national_polls] 1..M   or NULL    */
+  const int32_t* poll_pop_state;     /* [N_state_polls]    1..Pop or NULL    */
+  const int32_t* poll_pop_national;  /* [N_national_polls] 1..Pop or NULL    */
+  const int32_t* n_democrat_national;
+  const int32_t* n_two_share_national;
+  const int32_t* n_democrat_state;
+  const int32_t* n_two_share_state;
+  const double* unadjusted_national; /* in [0,1]; may be NULL for the no-mode variant */
+  const double* unadjusted_state;
+  const double* mu_b_prior;          /* [S] */
+  const double* state_weights;       /* [S] */
+  double sigma_c, sigma_m, sigma_pop;
+  double sigma_measure_noise_national, sigma_measure_noise_state, sigma_e_bias;
+  const double* state_covariance_0;  /* [S*S] column-major, symmetric positive definite */
+  double random_walk_scale, mu_b_T_scale, polling_bias_scale;
+} PotusData;
+
+/* Mirrors the cmdstanr `$sample()` argument names used at final_2016.R:533-541 plus Stan's
+ * defaults for what the reference never overrides (adapt_delta 0.8, max_treedepth 10, init 2). */
+typedef struct PotusConfig {
+  int32_t chains;          /* chains run by THIS sampler (this GPU)                                */
+  int32_t chain_id_offset; /* global id of its first chain: RNG streams are keyed by global id,   */
+                           /* so sharding chains over GPUs/ranks does not change any chain         */
+  int32_t iter_warmup;     /* default 500 */
+  int32_t iter_sampling;   /* default 500 */
+  int32_t keep_per_chain;  /* full draws (mu_b, ...) kept per chain, evenly thinned from the       */
+                           /* sampling iterations; 0 = keep all.  The 52 monitored scalars and the  */
+                           /* 7 sampler diagnostics are always kept for every iteration.           */
+  int32_t max_treedepth;   /* default 10 */
+  int32_t device;          /* CUDA device ordinal */
+  int32_t reserved;
+  uint64_t seed;           /* default 1843 (final_2016.R:535) */
+  double adapt_delta;      /* default 0.8 */
+  double init_radius;      /* default 2.0: inits ~ U(-r, r) on the unconstrained scale */
+} PotusConfig;
+
+typedef struct PotusStats {
+  int64_t n_leapfrog_total;      /* all chains, warm-up + sampling                           */
+  int64_t n_leapfrog_sampling;
+  int64_t n_divergent_sampling;
+  int64_t gpu_launches;          /* kernels launched by potus_run                            */
+  double seconds_total;          /* device time of potus_run (CUDA events)                   */
+  double seconds_warmup;
+  double seconds_sampling;
+  double mean_stepsize;          /* post-warm-up, mean over chains                           */
+  double mean_accept_stat;       /* sampling iterations                                      */
+  double mean_treedepth;
+  int32_t n_params;              /* unconstrained dimension D                                */
+  int32_t n_draws_kept;          /* chains * keep_per_chain                                  */
+} PotusStats;
+
+typedef struct PotusSampler PotusSampler;
+
+/* Validate `data` against the Stan data block, build device-side structures, draw inits. */
+int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
+/* Run warm-up + sampling for all chains; blocks until done. */
+int potus_run(PotusSampler* s);
+/* Number of doubles potus_get_draws would write for `par` (0 if unknown). */
+size_t potus_draws_size(const PotusSampler* s, const char* par);
+/* Copy kept draws of one quantity to host, shaped like rstan::extract(out, pars=par)[[1]]:
+ * R column-major with the draw index fastest, chains concatenated in chain order:
+ *   "mu_b" [draws,S,T]  "mu_c" [draws,P]  "mu_m" [draws,M]  "mu_pop" [draws,Pop]
+ *   "polling_bias" [draws,S]  "e_bias" [draws,T]  "predicted_score" [draws,T,S]
+ *   "theta" [draws,D] (unconstrained, Stan order)
+ *   "monitor" [iter_sampling*chains, S+1]  every sampling iteration: mu_b[,T] and national_mu_b_average[T]
+ *   "sampler_params" [(iter_warmup+iter_sampling)*chains, 7]
+ *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__          */
+int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
+int potus_get_stats(PotusSampler* s, PotusStats* stats);
+/* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py):
+ *   which = 0: kept draws   [chains*keep][draw_len]   (draw_len floats per draw, Stan block order:
+ *              mu_b | mu_c | mu_m | mu_pop | e_bias | polling_bias | theta)
+ *   which = 1: monitor      [chains][iter_sampling][S+1]
+ *   which = 2: sampler_params [chains][iter_warmup+iter_sampling][8] */
+int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n_floats);
+void potus_destroy(PotusSampler* s);
+const char* potus_last_error(void);
+
+/* Test hook: log density (constants dropped as Stan's `~` does, log(0.02) Jacobian constant
+ * excluded) and gradient for n_chains unconstrained vectors theta[n_chains][D] (Stan order),
+ * evaluated by the same device code the sampler uses. */
+int potus_logp_grad(const PotusData* data, const double* theta, int n_chains, double* lp, double* grad);
+/* Unconstrained dimension for a data list (15098 for the 2016 list). */
+int potus_num_params(const PotusData* data);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POTUS_B200_H */
