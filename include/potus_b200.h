@@ -25,6 +25,12 @@
 extern "C" {
 #endif
 
+#if defined(__GNUC__)
+#define POTUS_API __attribute__((visibility("default")))
+#else
+#define POTUS_API
+#endif
+
 #define POTUS_OK 0
 #define POTUS_ERR_INVALID_DATA (-1)   /* Stan data-block constraint violated (poll_model_2020.stan:9-23,37) */
 #define POTUS_ERR_UNSUPPORTED (-2)    /* problem size outside what the resident kernel handles */
@@ -97,11 +103,11 @@ typedef struct PotusStats {
 typedef struct PotusSampler PotusSampler;
 
 /* Validate `data` against the Stan data block, build device-side structures, draw inits. */
-int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
+POTUS_API int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
 /* Run warm-up + sampling for all chains; blocks until done. */
-int potus_run(PotusSampler* s);
+POTUS_API int potus_run(PotusSampler* s);
 /* Number of doubles potus_get_draws would write for `par` (0 if unknown). */
-size_t potus_draws_size(const PotusSampler* s, const char* par);
+POTUS_API size_t potus_draws_size(const PotusSampler* s, const char* par);
 /* Copy kept draws of one quantity to host, shaped like rstan::extract(out, pars=par)[[1]]:
  * R column-major with the draw index fastest, chains concatenated in chain order:
  *   "mu_b" [draws,S,T]  "mu_c" [draws,P]  "mu_m" [draws,M]  "mu_pop" [draws,Pop]
@@ -110,23 +116,23 @@ size_t potus_draws_size(const PotusSampler* s, const char* par);
  *   "monitor" [iter_sampling*chains, S+1]  every sampling iteration: mu_b[,T] and national_mu_b_average[T]
  *   "sampler_params" [(iter_warmup+iter_sampling)*chains, 7]
  *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__          */
-int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
-int potus_get_stats(PotusSampler* s, PotusStats* stats);
+POTUS_API int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
+POTUS_API int potus_get_stats(PotusSampler* s, PotusStats* stats);
 /* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py):
  *   which = 0: kept draws   [chains*keep][draw_len]   (draw_len floats per draw, Stan block order:
  *              mu_b | mu_c | mu_m | mu_pop | e_bias | polling_bias | theta)
  *   which = 1: monitor      [chains][iter_sampling][S+1]
  *   which = 2: sampler_params [chains][iter_warmup+iter_sampling][8] */
-int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n_floats);
-void potus_destroy(PotusSampler* s);
-const char* potus_last_error(void);
+POTUS_API int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n_floats);
+POTUS_API void potus_destroy(PotusSampler* s);
+POTUS_API const char* potus_last_error(void);
 
 /* Test hook: log density (constants dropped as Stan's `~` does, log(0.02) Jacobian constant
  * excluded) and gradient for n_chains unconstrained vectors theta[n_chains][D] (Stan order),
  * evaluated by the same device code the sampler uses. */
-int potus_logp_grad(const PotusData* data, const double* theta, int n_chains, double* lp, double* grad);
+POTUS_API int potus_logp_grad(const PotusData* data, const double* theta, int n_chains, double* lp, double* grad);
 /* Unconstrained dimension for a data list (15098 for the 2016 list). */
-int potus_num_params(const PotusData* data);
+POTUS_API int potus_num_params(const PotusData* data);
 
 #ifdef __cplusplus
 }

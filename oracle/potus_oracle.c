@@ -297,7 +297,8 @@ ORC_API void orc_rng_words(uint64_t seed, uint32_t chain, uint32_t idx, uint32_t
   out[0] = idx; out[1] = iter; out[2] = stream | (sub << 8); out[3] = chain;
   philox4x32_10(out, (uint32_t)seed, (uint32_t)(seed >> 32));
 }
-static inline double u01(uint32_t w) { return ((double)(w >> 8) + 0.5) * (1.0 / 16777216.0); }
+/* 23-bit uniforms: ((w>>9)+0.5)*2^-23 is exact in fp32 too, so the CUDA kernel draws the same numbers */
+static inline double u01(uint32_t w) { return ((double)(w >> 9) + 0.5) * (1.0 / 8388608.0); }
 static inline double rng_normal(uint64_t seed, uint32_t chain, uint32_t idx, uint32_t iter, uint32_t stream, uint32_t sub) {
   uint32_t w[4];
   orc_rng_words(seed, chain, idx, iter, stream, sub, w);

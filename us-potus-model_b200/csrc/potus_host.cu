@@ -1,0 +1,692 @@
+// Host side of the C-ABI (include/potus_b200.h): data validation (Stan's data-block constraints),
+// construction of the device-side model (Cholesky, UMMA operand planes, sorted polls, segment-sum
+// task lists, owner-layout maps), launches, and output reshaping to rstan::extract's layout.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+#include "../../include/potus_b200.h"
+#include "potus_layout.h"
+
+// (compiled as one translation unit with potus_kernel.cu through potus_lib.cu, which defines the kernels)
+using namespace potus;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CUDA_TRY(x)                                                                                         \
+  do {                                                                                                      \
+    cudaError_t e_ = (x);                                                                                   \
+    if (e_ != cudaSuccess)                                                                                  \
+      return fail(POTUS_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                         \
+  } while (0)
+
+namespace {
+
+struct Offsets { int zT, Z, c, m, pop, umu, urho, ze, xn, xs, zb, D; };
+
+struct HostModel {
+  ModelDev m{};
+  Offsets o{};
+  int S, T, P, M, Pop, Nn, Ns, N, full;
+  std::vector<int32_t> map_i2s;            // [VEC]
+  std::vector<void*> dev_allocs;
+  double nat_sd;
+};
+
+template <class Tv>
+int upload(HostModel& hm, const std::vector<Tv>& v, const void** out) {
+  void* d = nullptr;
+  size_t bytes = std::max<size_t>(v.size() * sizeof(Tv), 16);
+  CUDA_TRY(cudaMalloc(&d, bytes));
+  hm.dev_allocs.push_back(d);
+  if (!v.empty()) CUDA_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+  *out = d;
+  return POTUS_OK;
+}
+
+void free_model(HostModel& hm) {
+  for (void* p : hm.dev_allocs) cudaFree(p);
+  hm.dev_allocs.clear();
+}
+
+// Stan data-block constraints, poll_model_2020.stan:2-40
+int validate(const PotusData* d) {
+  char buf[256];
+  auto bad = [&](const char* what, long i, double v, const char* cons) {
+    snprintf(buf, sizeof buf, "Exception: poll_model_2020: %s[%ld] is %g, but must be %s", what, i + 1, v, cons);
+    return fail(POTUS_ERR_INVALID_DATA, buf);
+  };
+  if (!d) return fail(POTUS_ERR_INVALID_DATA, "data is NULL");
+  if (d->S < 1 || d->T < 2 || d->P < 1 || d->N_state_polls < 0 || d->N_national_polls < 0)
+    return fail(POTUS_ERR_INVALID_DATA, "S, T, P, N_state_polls, N_national_polls must be positive sizes");
+  const bool full = d->poll_mode_state != nullptr;
+  if (full && (!d->poll_mode_national || !d->poll_pop_state || !d->poll_pop_national || !d->unadjusted_state || !d->unadjusted_national))
+    return fail(POTUS_ERR_INVALID_DATA, "poll_mode_*/poll_pop_*/unadjusted_* must be given together (full model) or all absent");
+  if (!d->state || !d->day_state || !d->day_national || !d->poll_state || !d->poll_national || !d->n_democrat_national ||
+      !d->n_two_share_national || !d->n_democrat_state || !d->n_two_share_state || !d->mu_b_prior || !d->state_weights ||
+      !d->state_covariance_0)
+    return fail(POTUS_ERR_INVALID_DATA, "a required data vector is NULL");
+  for (int i = 0; i < d->N_state_polls; ++i) {
+    if (d->state[i] < 1 || d->state[i] > d->S + 1) return bad("state", i, d->state[i], "in [1, S+1]");
+    if (d->state[i] > d->S) return bad("state", i, d->state[i], "<= S (mu_b has S rows; index S+1 would fault in Stan)");
+    if (d->day_state[i] < 1 || d->day_state[i] > d->T) return bad("day_state", i, d->day_state[i], "in [1, T]");
+    if (d->poll_state[i] < 1 || d->poll_state[i] > d->P) return bad("poll_state", i, d->poll_state[i], "in [1, P]");
+    if (d->n_two_share_state[i] < 0) return bad("n_two_share_state", i, d->n_two_share_state[i], ">= 0");
+    if (d->n_democrat_state[i] < 0 || d->n_democrat_state[i] > d->n_two_share_state[i])
+      return bad("n_democrat_state", i, d->n_democrat_state[i], "in [0, n_two_share_state]");
+    if (full) {
+      if (d->poll_mode_state[i] < 1 || d->poll_mode_state[i] > d->M) return bad("poll_mode_state", i, d->poll_mode_state[i], "in [1, M]");
+      if (d->poll_pop_state[i] < 1 || d->poll_pop_state[i] > d->Pop) return bad("poll_pop_state", i, d->poll_pop_state[i], "in [1, Pop]");
+      if (!(d->unadjusted_state[i] >= 0 && d->unadjusted_state[i] <= 1)) return bad("unadjusted_state", i, d->unadjusted_state[i], "in [0, 1]");
+    }
+  }
+  for (int i = 0; i < d->N_national_polls; ++i) {
+    if (d->day_national[i] < 1 || d->day_national[i] > d->T) return bad("day_national", i, d->day_national[i], "in [1, T]");
+    if (d->poll_national[i] < 1 || d->poll_national[i] > d->P) return bad("poll_national", i, d->poll_national[i], "in [1, P]");
+    if (d->n_two_share_national[i] < 0) return bad("n_two_share_national", i, d->n_two_share_national[i], ">= 0");
+    if (d->n_democrat_national[i] < 0 || d->n_democrat_national[i] > d->n_two_share_national[i])
+      return bad("n_democrat_national", i, d->n_democrat_national[i], "in [0, n_two_share_national]");
+    if (full) {
+      if (d->poll_mode_national[i] < 1 || d->poll_mode_national[i] > d->M) return bad("poll_mode_national", i, d->poll_mode_national[i], "in [1, M]");
+      if (d->poll_pop_national[i] < 1 || d->poll_pop_national[i] > d->Pop) return bad("poll_pop_national", i, d->poll_pop_national[i], "in [1, Pop]");
+      if (!(d->unadjusted_national[i] >= 0 && d->unadjusted_national[i] <= 1)) return bad("unadjusted_national", i, d->unadjusted_national[i], "in [0, 1]");
+    }
+  }
+  const int S = d->S;  // cov_matrix[S] state_covariance_0: symmetric (Stan's 1e-8 relative tolerance), PD checked by Cholesky
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < i; ++j) {
+      double a = d->state_covariance_0[i + S * j], b = d->state_covariance_0[j + S * i];
+      if (std::fabs(a - b) > 1e-8 * std::max(1.0, std::max(std::fabs(a), std::fabs(b)))) {
+        snprintf(buf, sizeof buf, "Exception: poll_model_2020: state_covariance_0 is not symmetric. state_covariance_0[%d,%d] = %g, but [%d,%d] = %g", i + 1, j + 1, a, j + 1, i + 1, b);
+        return fail(POTUS_ERR_INVALID_DATA, buf);
+      }
+    }
+  return POTUS_OK;
+}
+
+int check_supported(const PotusData* d) {
+  char buf[256];
+  const bool full = d->poll_mode_state != nullptr;
+  const int N = d->N_state_polls + d->N_national_polls;
+  if (d->S > MAX_S || d->T > MAX_T || N > NPOLL_CAP || d->P > 1023 || (full && (d->M > MAX_MODE || d->Pop > MAX_MODE))) {
+    snprintf(buf, sizeof buf,
+             "problem size S=%d T=%d N=%d P=%d M=%d Pop=%d is outside the resident kernel's limits (S<=%d, T<=%d, N<=%d, P<=1023, M,Pop<=%d); "
+             "the streaming large-S/T variant (BASELINE config 5) is not built yet",
+             d->S, d->T, N, d->P, d->M, d->Pop, MAX_S, MAX_T, NPOLL_CAP, MAX_MODE);
+    return fail(POTUS_ERR_UNSUPPORTED, buf);
+  }
+  if (full)
+    for (int pass = 0; pass < 2; ++pass) {
+      const double* u = pass ? d->unadjusted_national : d->unadjusted_state;
+      int n = pass ? d->N_national_polls : d->N_state_polls;
+      for (int i = 0; i < n; ++i)
+        if (u[i] != 0.0 && u[i] != 1.0) return fail(POTUS_ERR_UNSUPPORTED, "unadjusted_* must be 0 or 1 (fractional values are not supported)");
+    }
+  return POTUS_OK;
+}
+
+void split_half(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn((x - __half2float(hi)) * 2048.0f);
+}
+
+int build_model(const PotusData* d, HostModel& hm) {
+  int rc = validate(d);
+  if (rc) return rc;
+  rc = check_supported(d);
+  if (rc) return rc;
+  const int S = d->S, T = d->T, P = d->P, Ns = d->N_state_polls, Nn = d->N_national_polls, N = Ns + Nn;
+  const bool full = d->poll_mode_state != nullptr;
+  const int M = full ? d->M : 0, Pop = full ? d->Pop : 0;
+  hm.S = S; hm.T = T; hm.P = P; hm.M = d->M; hm.Pop = d->Pop; hm.Ns = Ns; hm.Nn = Nn; hm.N = N; hm.full = full;
+  // Stan unconstrained order (poll_model_2020.stan:56-69)
+  Offsets& o = hm.o;
+  int off = 0;
+  o.zT = off; off += S;
+  o.Z = off; off += S * T;
+  o.c = off; off += P;
+  o.m = o.pop = o.umu = o.urho = o.ze = -1;
+  if (full) { o.m = off; off += M; o.pop = off; off += Pop; o.umu = off; off += 1; o.urho = off; off += 1; o.ze = off; off += T; }
+  o.xn = off; off += Nn;
+  o.xs = off; off += Ns;
+  o.zb = off; off += S;
+  o.D = off;
+
+  // ---- transformed data (poll_model_2020.stan:42-55): nat_sd, L0 = chol(Sigma0), three scalars
+  std::vector<double> L0((size_t)S * S, 0.0), w(d->state_weights, d->state_weights + S);
+  double nat = 0;
+  for (int i = 0; i < S; ++i)
+    for (int j = 0; j < S; ++j) nat += w[i] * d->state_covariance_0[i + S * j] * w[j];
+  if (!(nat > 0)) return fail(POTUS_ERR_INVALID_DATA, "state_weights' * state_covariance_0 * state_weights must be positive");
+  nat = std::sqrt(nat);
+  hm.nat_sd = nat;
+  for (int j = 0; j < S; ++j) {
+    double s = d->state_covariance_0[j + S * j];
+    for (int k = 0; k < j; ++k) s -= L0[j * S + k] * L0[j * S + k];
+    if (!(s > 0)) return fail(POTUS_ERR_INVALID_DATA, "Exception: poll_model_2020: state_covariance_0 is not positive definite.");
+    double ljj = std::sqrt(s);
+    L0[j * S + j] = ljj;
+    for (int i = j + 1; i < S; ++i) {
+      double v = d->state_covariance_0[i + S * j];
+      for (int k = 0; k < j; ++k) v -= L0[i * S + k] * L0[j * S + k];
+      L0[i * S + j] = v / ljj;
+    }
+  }
+  ModelDev& m = hm.m;
+  m.S = S; m.T = T; m.P = P; m.M = M; m.Pop = Pop; m.Nn = Nn; m.Ns = Ns; m.N = N; m.full = full; m.D = o.D;
+  m.npair = (S + 1) / 2;
+  m.a_b = (float)(d->polling_bias_scale / nat); m.a_T = (float)(d->mu_b_T_scale / nat); m.a_w = (float)(d->random_walk_scale / nat);
+  m.sig_c = (float)d->sigma_c; m.sig_m = (float)d->sigma_m; m.sig_pop = (float)d->sigma_pop;
+  m.sig_n = (float)d->sigma_measure_noise_national; m.sig_s = (float)d->sigma_measure_noise_state; m.sig_e = (float)d->sigma_e_bias;
+  // nz block layout
+  int nz = 0;
+  m.nz_zT = nz; nz += S;
+  m.nz_c = nz; nz += P;
+  m.nz_m = m.nz_pop = m.nz_umu = m.nz_urho = m.nz_ze = 0;
+  if (full) { m.nz_m = nz; nz += M; m.nz_pop = nz; nz += Pop; m.nz_umu = nz; nz += 1; m.nz_urho = nz; nz += 1; m.nz_ze = nz; nz += T; }
+  m.nz_x = nz; nz += N;
+  m.nz_zb = nz; nz += S;
+  m.NZ = nz;
+  if (nz > NZ_CAP) return fail(POTUS_ERR_UNSUPPORTED, "too many non-walk parameters for the resident kernel (NZ > 3072)");
+
+  // ---- polls sorted by (day, state); national polls by day
+  std::vector<int> ord_s(Ns), ord_n(Nn);
+  std::iota(ord_s.begin(), ord_s.end(), 0);
+  std::iota(ord_n.begin(), ord_n.end(), 0);
+  std::stable_sort(ord_s.begin(), ord_s.end(), [&](int a, int b) {
+    if (d->day_state[a] != d->day_state[b]) return d->day_state[a] < d->day_state[b];
+    return d->state[a] < d->state[b];
+  });
+  std::stable_sort(ord_n.begin(), ord_n.end(), [&](int a, int b) { return d->day_national[a] < d->day_national[b]; });
+  struct HP { int s, dd, p, mo, po, un; double n, y; int stan_x; };
+  std::vector<HP> hp(N);
+  double sum_n = 0;
+  for (int k = 0; k < Ns; ++k) {
+    int i = ord_s[k];
+    hp[k] = HP{d->state[i] - 1, d->day_state[i] - 1, d->poll_state[i] - 1, full ? d->poll_mode_state[i] - 1 : 0,
+               full ? d->poll_pop_state[i] - 1 : 0, full ? (int)d->unadjusted_state[i] : 0, (double)d->n_two_share_state[i],
+               (double)d->n_democrat_state[i], o.xs + i};
+    sum_n += hp[k].n;
+  }
+  for (int k = 0; k < Nn; ++k) {
+    int j = ord_n[k];
+    hp[Ns + k] = HP{NAT_COL, d->day_national[j] - 1, d->poll_national[j] - 1, full ? d->poll_mode_national[j] - 1 : 0,
+                    full ? d->poll_pop_national[j] - 1 : 0, full ? (int)d->unadjusted_national[j] : 0,
+                    (double)d->n_two_share_national[j], (double)d->n_democrat_national[j], o.xn + j};
+    sum_n += hp[Ns + k].n;
+  }
+  std::vector<uint32_t> pk(5 * (size_t)NPOLL_CAP, 0u);
+  double lp_const = 0;
+  for (int k = 0; k < N; ++k) {
+    const HP& q = hp[k];
+    double frac = q.n > 0 ? q.y / q.n : 0.5;
+    double fc = std::min(std::max(frac, 1e-4), 1.0 - 1e-4);
+    float eh = (float)std::log(fc / (1.0 - fc));
+    float ph = (float)(1.0 / (1.0 + std::exp(-(double)eh)));
+    float rh = (float)(frac - (double)ph);
+    float nf = (float)q.n;
+    pk[k] = pack_poll(q.s, q.dd, q.p, q.mo, q.po, q.un);
+    memcpy(&pk[1 * NPOLL_CAP + k], &nf, 4);
+    memcpy(&pk[2 * NPOLL_CAP + k], &eh, 4);
+    memcpy(&pk[3 * NPOLL_CAP + k], &ph, 4);
+    memcpy(&pk[4 * NPOLL_CAP + k], &rh, 4);
+    // centring constant of the function the kernel evaluates: n[(ph+rh)(eta-eh) - log1p(ph expm1(eta-eh))] = ll(eta) - ll(eh)
+    double ehd = eh, sp = (ehd > 0 ? ehd : 0) + std::log1p(std::exp(-std::fabs(ehd)));
+    lp_const += q.y * ehd - q.n * sp;
+  }
+  m.lp_const = lp_const;
+  {  // G operand scale: |sum of residuals| <= sum n must stay inside fp16 range
+    double sc = 1.0;
+    while (sum_n * sc > 32768.0) sc *= 0.5;
+    m.scale_G = (float)sc; m.inv_scale_G = (float)(1.0 / sc);
+  }
+
+  // ---- X planes: X[r][c], r = output state (row 51 = national: w^T L0), c = k; scaled by 256; K-major canonical layout
+  std::vector<__half> bt(2 * (size_t)B_PLANE / 2, __float2half_rn(0.f));
+  auto boff = [](int r, int c) { return (size_t)((c / 8) * B_LBO + (r / 8) * B_SBO + (r % 8) * 16 + (c % 8) * 2) / 2; };
+  for (int r = 0; r < 64; ++r)
+    for (int c = 0; c < 64; ++c) {
+      double v = 0;
+      if (r < S && c < S) v = L0[r * S + c];
+      else if (r == NAT_COL && c < S) { for (int s = 0; s < S; ++s) v += w[s] * L0[s * S + c]; }
+      __half hi, lo;
+      split_half((float)(v * 256.0), hi, lo);
+      bt[boff(r, c)] = hi;
+      bt[B_PLANE / 2 + boff(r, c)] = lo;
+    }
+  std::vector<float> prior(64, 0.f);
+  double wp = 0;
+  for (int s = 0; s < S; ++s) { prior[s] = (float)d->mu_b_prior[s]; wp += w[s] * d->mu_b_prior[s]; }
+  prior[NAT_COL] = (float)wp;
+
+  // ---- segment-sum tasks
+  std::vector<uint32_t> t1;
+  std::vector<uint2> t2;
+  std::vector<uint16_t> ids;
+  auto add_segments = [&](int type, int start, int cnt, int& pstart, int& pcnt) {
+    pstart = (int)t1.size(); pcnt = 0;
+    while (cnt > 0) {
+      int c = std::min(cnt, 32);
+      t1.push_back((uint32_t)start | ((uint32_t)c << 16) | ((uint32_t)type << 24));
+      start += c; cnt -= c; ++pcnt;
+    }
+  };
+  bool seg_overflow = false;
+  auto add_final = [&](int kind, int dest, int pstart, int pcnt) {
+    if (pcnt > 255 || pstart > 65535) seg_overflow = true;
+    t2.push_back(make_uint2((uint32_t)pstart | ((uint32_t)pcnt << 16) | ((uint32_t)kind << 24), (uint32_t)dest));
+  };
+  // cells (state polls are sorted by day then state, national by day: groups are contiguous)
+  for (int k = 0; k < N;) {
+    int e = k;
+    while (e < N && hp[e].dd == hp[k].dd && hp[e].s == hp[k].s && ((e < Ns) == (k < Ns))) ++e;
+    int ps, pc;
+    add_segments(0, k, e - k, ps, pc);
+    add_final(0, hp[k].dd * 64 + hp[k].s, ps, pc);
+    k = e;
+  }
+  if (full) {  // g_e[t] = sum over polls of day t of unadjusted * r
+    std::vector<int> s0(T + 1, 0), n0(T + 1, 0);
+    for (int k = 0; k < Ns; ++k) s0[hp[k].dd + 1]++;
+    for (int k = 0; k < Nn; ++k) n0[hp[Ns + k].dd + 1]++;
+    for (int t = 0; t < T; ++t) { s0[t + 1] += s0[t]; n0[t + 1] += n0[t]; }
+    for (int t = 0; t < T; ++t) {
+      int ps, pc, ps2, pc2;
+      add_segments(1, s0[t], s0[t + 1] - s0[t], ps, pc);
+      add_segments(1, Ns + n0[t], n0[t + 1] - n0[t], ps2, pc2);
+      add_final(2, t, ps, pc + pc2);  // segments are appended back to back
+    }
+  }
+  {  // pollsters
+    std::vector<std::vector<uint16_t>> byp(P);
+    for (int k = 0; k < N; ++k) byp[hp[k].p].push_back((uint16_t)k);
+    for (int p = 0; p < P; ++p) {
+      int st = (int)ids.size(), ps, pc;
+      ids.insert(ids.end(), byp[p].begin(), byp[p].end());
+      add_segments(2, st, (int)byp[p].size(), ps, pc);
+      add_final(1, m.nz_c + p, ps, pc);
+    }
+    std::vector<std::vector<uint16_t>> bys(S);
+    for (int k = 0; k < Ns; ++k) bys[hp[k].s].push_back((uint16_t)k);
+    for (int s = 0; s < S; ++s) {
+      int st = (int)ids.size(), ps, pc;
+      ids.insert(ids.end(), bys[s].begin(), bys[s].end());
+      add_segments(2, st, (int)bys[s].size(), ps, pc);
+      add_final(0, PB_ROW * 64 + s, ps, pc);
+    }
+  }
+  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || ids.size() > 65535)
+    return fail(POTUS_ERR_UNSUPPORTED, "poll structure needs more segment tasks than the resident kernel holds");
+  if (seg_overflow) return fail(POTUS_ERR_UNSUPPORTED, "a poll group needs more than 255 segments");
+  m.n_t1 = (int)t1.size(); m.n_t2 = (int)t2.size();
+
+  // ---- owner-layout map: internal slot -> Stan unconstrained index
+  hm.map_i2s.assign(VEC, -1);
+  for (int tid = 0; tid < NT; ++tid) {
+    int wq = tid >> 5, l = tid & 31;
+    for (int e = 0; e < EPT; ++e) {
+      int idx = -1;
+      if (l < ZLANES) {
+        int s = 2 * l + (e & 1), t = 16 * wq + (e >> 1);
+        if (s < S && t < T) idx = o.Z + s + S * t;
+      } else {
+        int k = (wq * NZ_LANES + (l - ZLANES)) * EPT + e;
+        if (k < m.NZ) {
+          if (k < m.nz_c) idx = o.zT + (k - m.nz_zT);
+          else if (k < m.nz_c + P) idx = o.c + (k - m.nz_c);
+          else if (full && k < m.nz_pop) idx = o.m + (k - m.nz_m);
+          else if (full && k < m.nz_umu) idx = o.pop + (k - m.nz_pop);
+          else if (full && k == m.nz_umu) idx = o.umu;
+          else if (full && k == m.nz_urho) idx = o.urho;
+          else if (full && k < m.nz_x) idx = o.ze + (k - m.nz_ze);
+          else if (k < m.nz_zb) idx = hp[k - m.nz_x].stan_x;
+          else idx = o.zb + (k - m.nz_zb);
+        }
+      }
+      hm.map_i2s[e * NT + tid] = idx;
+    }
+  }
+  {  // every Stan index must be covered exactly once
+    std::vector<int> cnt(o.D, 0);
+    for (int v : hm.map_i2s) if (v >= 0) { if (v >= o.D) return fail(POTUS_ERR_STATE, "internal map out of range"); cnt[v]++; }
+    for (int i = 0; i < o.D; ++i) if (cnt[i] != 1) return fail(POTUS_ERR_STATE, "internal layout map is not a bijection");
+  }
+  const void* p;
+  if ((rc = upload(hm, bt, &p))) return rc; m.btiles = p;
+  if ((rc = upload(hm, pk, &p))) return rc; m.pk = (const uint32_t*)p;
+  if ((rc = upload(hm, prior, &p))) return rc; m.prior = (const float*)p;
+  if ((rc = upload(hm, t1, &p))) return rc; m.t1 = (const uint32_t*)p;
+  if ((rc = upload(hm, t2, &p))) return rc; m.t2 = (const uint2*)p;
+  if ((rc = upload(hm, ids, &p))) return rc; m.ids = (const uint16_t*)p;
+  if ((rc = upload(hm, hm.map_i2s, &p))) return rc; m.map_i2s = (const int32_t*)p;
+  return POTUS_OK;
+}
+
+int check_device(int device, int* n_sm) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return fail(POTUS_ERR_CUDA, std::string("no CUDA device available (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+  if (device < 0 || device >= count) return fail(POTUS_ERR_CUDA, "device ordinal out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "device %d (%s) is sm_%d%d; this library contains sm_100a code only", device, prop.name, prop.major, prop.minor);
+    return fail(POTUS_ERR_CUDA, buf);
+  }
+  if (n_sm) *n_sm = prop.multiProcessorCount;
+  return POTUS_OK;
+}
+
+constexpr int SMEM_BYTES = (int)SM_TOTAL + 128;
+
+}  // namespace
+
+struct PotusSampler {
+  HostModel hm;
+  PotusConfig cfg;
+  int n_sm = 0, grid = 0, draw_len = 0, keep = 0, keep_every = 1;
+  float *q = nullptr, *sqrt_m = nullptr, *wf_mean = nullptr, *wf_m2 = nullptr, *workspace = nullptr;
+  ChainState* cs = nullptr;
+  int* queue = nullptr;
+  float *draws = nullptr, *monitor = nullptr, *sparams = nullptr;
+  bool ran = false;
+  PotusStats stats{};
+  std::vector<float> h_draws, h_monitor, h_sparams;
+  bool have_host = false;
+};
+
+extern "C" {
+
+const char* potus_last_error(void) { return g_err.c_str(); }
+
+int potus_num_params(const PotusData* d) {
+  if (!d) return 0;
+  const bool full = d->poll_mode_state != nullptr;
+  int D = d->S + d->S * d->T + d->P + d->N_national_polls + d->N_state_polls + d->S;
+  if (full) D += d->M + d->Pop + 2 + d->T;
+  return D;
+}
+
+void potus_destroy(PotusSampler* s) {
+  if (!s) return;
+  free_model(s->hm);
+  cudaFree(s->q); cudaFree(s->sqrt_m); cudaFree(s->wf_mean); cudaFree(s->wf_m2); cudaFree(s->workspace);
+  cudaFree(s->cs); cudaFree(s->queue); cudaFree(s->draws); cudaFree(s->monitor); cudaFree(s->sparams);
+  delete s;
+}
+
+int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out) {
+  if (!out) return fail(POTUS_ERR_STATE, "out is NULL");
+  *out = nullptr;
+  if (!config) return fail(POTUS_ERR_STATE, "config is NULL");
+  if (config->chains < 1 || config->iter_warmup < 0 || config->iter_sampling < 0 || config->max_treedepth < 1 ||
+      config->max_treedepth > MAX_DEPTH_CAP)
+    return fail(POTUS_ERR_STATE, "config: chains >= 1, iter_* >= 0, 1 <= max_treedepth <= 10 required");
+  int rc = validate(data);
+  if (rc) return rc;
+  rc = check_supported(data);
+  if (rc) return rc;
+  int n_sm = 0;
+  rc = check_device(config->device, &n_sm);
+  if (rc) return rc;
+  PotusSampler* s = new PotusSampler();
+  s->cfg = *config;
+  s->n_sm = n_sm;
+  rc = build_model(data, s->hm);
+  if (rc) { potus_destroy(s); return rc; }
+  const ModelDev& m = s->hm.m;
+  const int C = config->chains;
+  s->keep = config->keep_per_chain <= 0 ? config->iter_sampling : std::min(config->keep_per_chain, config->iter_sampling);
+  s->keep_every = s->keep > 0 ? config->iter_sampling / s->keep : 1;
+  s->draw_len = m.S * m.T + m.P + s->hm.M + s->hm.Pop + m.T + m.S + m.D;
+  s->grid = std::min(C, n_sm);
+  const size_t vb = (size_t)C * VEC * sizeof(float);
+  auto alloc = [&](void** p, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) { char b[160]; snprintf(b, sizeof b, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return fail(POTUS_ERR_CUDA, b); }
+    return cudaMemset(*p, 0, std::max<size_t>(bytes, 16)) == cudaSuccess ? POTUS_OK : fail(POTUS_ERR_CUDA, "cudaMemset failed");
+  };
+  const int n_it = config->iter_warmup + config->iter_sampling;
+  if ((rc = alloc((void**)&s->q, vb)) || (rc = alloc((void**)&s->sqrt_m, vb)) || (rc = alloc((void**)&s->wf_mean, vb)) ||
+      (rc = alloc((void**)&s->wf_m2, vb)) || (rc = alloc((void**)&s->workspace, (size_t)s->grid * NSLOT * VEC * sizeof(float))) ||
+      (rc = alloc((void**)&s->cs, (size_t)C * sizeof(ChainState))) || (rc = alloc((void**)&s->queue, sizeof(int))) ||
+      (rc = alloc((void**)&s->draws, (size_t)C * s->keep * s->draw_len * sizeof(float))) ||
+      (rc = alloc((void**)&s->monitor, (size_t)C * config->iter_sampling * (m.S + 1) * sizeof(float))) ||
+      (rc = alloc((void**)&s->sparams, (size_t)C * n_it * 8 * sizeof(float)))) {
+    potus_destroy(s);
+    return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute(potus_nuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) { potus_destroy(s); return fail(POTUS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+  *out = s;
+  return POTUS_OK;
+}
+
+static RunArgs make_args(PotusSampler* s, int it0, int it1, int do_init) {
+  RunArgs a{};
+  a.m = s->hm.m;
+  a.n_chains = s->cfg.chains; a.chain_id_offset = s->cfg.chain_id_offset;
+  a.iter_begin = it0; a.iter_end = it1; a.iter_warmup = s->cfg.iter_warmup; a.iter_sampling = s->cfg.iter_sampling;
+  a.max_depth = s->cfg.max_treedepth; a.do_init = do_init;
+  a.keep_every = s->keep_every; a.keep_per_chain = s->keep; a.draw_len = s->draw_len;
+  // Stan windowed_adaptation defaults (75 / 50 / 25), and its fallback rule for short warm-ups
+  int nw = s->cfg.iter_warmup, ib = 75, tb = 50, bw = 25;
+  if (nw < 20) { ib = nw; tb = 0; bw = 0; }
+  else if (ib + bw + tb > nw) { ib = (int)(0.15 * nw); tb = (int)(0.1 * nw); bw = nw - (ib + tb); }
+  a.w_init_buffer = ib; a.w_term_buffer = tb; a.w_base_window = bw;
+  a.seed = s->cfg.seed; a.adapt_delta = (float)s->cfg.adapt_delta; a.init_radius = (float)s->cfg.init_radius;
+  a.q = s->q; a.sqrt_m = s->sqrt_m; a.wf_mean = s->wf_mean; a.wf_m2 = s->wf_m2; a.cs = s->cs; a.workspace = s->workspace;
+  a.queue = s->queue; a.draws = s->draws; a.monitor = s->monitor; a.sampler_params = s->sparams;
+  return a;
+}
+
+int potus_run(PotusSampler* s) {
+  if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  cudaEvent_t e0, e1, e2;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventCreate(&e2));
+  const int nw = s->cfg.iter_warmup, nt = nw + s->cfg.iter_sampling;
+  int launches = 0;
+  CUDA_TRY(cudaEventRecord(e0));
+  {
+    CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
+    RunArgs a = make_args(s, 0, nw, 1);
+    potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  CUDA_TRY(cudaEventRecord(e1));
+  if (nt > nw) {
+    CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
+    RunArgs a = make_args(s, nw, nt, 0);
+    potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    ++launches;
+  }
+  CUDA_TRY(cudaEventRecord(e2));
+  CUDA_TRY(cudaEventSynchronize(e2));
+  CUDA_TRY(cudaGetLastError());
+  float ms01 = 0, ms12 = 0;
+  CUDA_TRY(cudaEventElapsedTime(&ms01, e0, e1)); CUDA_TRY(cudaEventElapsedTime(&ms12, e1, e2));
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  // summary statistics from the per-iteration sampler diagnostics
+  const int C = s->cfg.chains;
+  s->h_sparams.resize((size_t)C * nt * 8);
+  CUDA_TRY(cudaMemcpy(s->h_sparams.data(), s->sparams, s->h_sparams.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  std::vector<ChainState> hcs(C);
+  CUDA_TRY(cudaMemcpy(hcs.data(), s->cs, (size_t)C * sizeof(ChainState), cudaMemcpyDeviceToHost));
+  PotusStats& st = s->stats;
+  st = PotusStats{};
+  double acc = 0, dep = 0, eps = 0;
+  for (int c = 0; c < C; ++c) {
+    if (hcs[c].status != 0) return fail(POTUS_ERR_INIT, "a chain found no finite initial point in 100 attempts (Stan: 'Initialization failed')");
+    for (int it = 0; it < nt; ++it) {
+      const float* p = &s->h_sparams[((size_t)c * nt + it) * 8];
+      st.n_leapfrog_total += (int64_t)p[4];
+      if (it >= nw) { st.n_leapfrog_sampling += (int64_t)p[4]; st.n_divergent_sampling += (int64_t)p[5]; acc += p[1]; dep += p[3]; }
+    }
+    eps += hcs[c].eps;
+  }
+  const double ns = (double)C * std::max(1, nt - nw);
+  st.mean_accept_stat = acc / ns; st.mean_treedepth = dep / ns; st.mean_stepsize = eps / C;
+  st.gpu_launches = launches;
+  st.seconds_warmup = ms01 * 1e-3; st.seconds_sampling = ms12 * 1e-3; st.seconds_total = (ms01 + ms12) * 1e-3;
+  st.n_params = s->hm.m.D; st.n_draws_kept = C * s->keep;
+  s->ran = true; s->have_host = false;
+  return POTUS_OK;
+}
+
+int potus_get_stats(PotusSampler* s, PotusStats* out) {
+  if (!s || !out) return fail(POTUS_ERR_STATE, "NULL argument");
+  if (!s->ran) return fail(POTUS_ERR_STATE, "potus_run has not completed");
+  *out = s->stats;
+  return POTUS_OK;
+}
+
+int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n) {
+  if (!s || !dptr || !n) return fail(POTUS_ERR_STATE, "NULL argument");
+  const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling;
+  switch (which) {
+    case 0: *dptr = s->draws; *n = (size_t)C * s->keep * s->draw_len; break;
+    case 1: *dptr = s->monitor; *n = (size_t)C * s->cfg.iter_sampling * (s->hm.m.S + 1); break;
+    case 2: *dptr = s->sparams; *n = (size_t)C * nt * 8; break;
+    default: return fail(POTUS_ERR_STATE, "unknown buffer id");
+  }
+  return POTUS_OK;
+}
+
+struct ParInfo { size_t off, len; bool exists; };
+static bool par_info(const PotusSampler* s, const char* par, ParInfo& pi) {
+  const ModelDev& m = s->hm.m;
+  const size_t ST = (size_t)m.S * m.T;
+  size_t o = 0;
+  const std::string p = par ? par : "";
+  auto hit = [&](const char* nm, size_t len, bool ex) { bool h = (p == nm); if (h) { pi.off = o; pi.len = len; pi.exists = ex; } o += len; return h; };
+  if (hit("mu_b", ST, true)) return true;
+  if (hit("mu_c", m.P, true)) return true;
+  if (hit("mu_m", s->hm.M, s->hm.full)) return true;
+  if (hit("mu_pop", s->hm.Pop, s->hm.full)) return true;
+  if (hit("e_bias", m.T, s->hm.full)) return true;
+  if (hit("polling_bias", m.S, true)) return true;
+  if (hit("theta", m.D, true)) return true;
+  return false;
+}
+
+size_t potus_draws_size(const PotusSampler* s, const char* par) {
+  if (!s || !par) return 0;
+  const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling;
+  const std::string p = par;
+  if (p == "monitor") return (size_t)C * s->cfg.iter_sampling * (s->hm.m.S + 1);
+  if (p == "sampler_params") return (size_t)C * nt * 7;
+  if (p == "predicted_score") return (size_t)C * s->keep * s->hm.m.S * s->hm.m.T;
+  ParInfo pi;
+  if (!par_info(s, par, pi) || !pi.exists) return 0;
+  return (size_t)C * s->keep * pi.len;
+}
+
+int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
+  if (!s || !par || !out) return fail(POTUS_ERR_STATE, "NULL argument");
+  if (!s->ran) return fail(POTUS_ERR_STATE, "potus_run has not completed");
+  const size_t need = potus_draws_size(s, par);
+  if (need == 0) return fail(POTUS_ERR_STATE, std::string("unknown quantity '") + par + "'");
+  if (n < need) return fail(POTUS_ERR_STATE, "output buffer too small");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling, S = s->hm.m.S, T = s->hm.m.T;
+  const std::string p = par;
+  if (p == "sampler_params") {  // [(iter)*chains, 7], row index = chain*nt + it (draw-fastest within a column)
+    const size_t R = (size_t)C * nt;
+    for (size_t r = 0; r < R; ++r)
+      for (int k = 0; k < 7; ++k) out[r + R * k] = s->h_sparams[r * 8 + k];
+    return POTUS_OK;
+  }
+  if (p == "monitor") {
+    const size_t R = (size_t)C * s->cfg.iter_sampling;
+    s->h_monitor.resize(R * (S + 1));
+    CUDA_TRY(cudaMemcpy(s->h_monitor.data(), s->monitor, s->h_monitor.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < R; ++r)
+      for (int k = 0; k <= S; ++k) out[r + R * k] = s->h_monitor[r * (S + 1) + k];
+    return POTUS_OK;
+  }
+  if (!s->have_host) {
+    s->h_draws.resize((size_t)C * s->keep * s->draw_len);
+    CUDA_TRY(cudaMemcpy(s->h_draws.data(), s->draws, s->h_draws.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    s->have_host = true;
+  }
+  const size_t R = (size_t)C * s->keep;
+  if (p == "predicted_score") {  // [draws, T, S] = inv_logit(mu_b[s,t]); poll_model_2020.stan:136-139
+    for (size_t r = 0; r < R; ++r) {
+      const float* dr = &s->h_draws[r * s->draw_len];
+      for (int t = 0; t < T; ++t)
+        for (int st = 0; st < S; ++st) {
+          double x = dr[st + (size_t)S * t];
+          out[r + R * ((size_t)t + (size_t)T * st)] = 1.0 / (1.0 + std::exp(-x));
+        }
+    }
+    return POTUS_OK;
+  }
+  ParInfo pi;
+  par_info(s, par, pi);
+  for (size_t r = 0; r < R; ++r) {
+    const float* dr = &s->h_draws[r * s->draw_len + pi.off];
+    for (size_t k = 0; k < pi.len; ++k) out[r + R * k] = dr[k];  // mu_b: k = s + S*t == R's [draw, s, t] order
+  }
+  return POTUS_OK;
+}
+
+int potus_logp_grad(const PotusData* data, const double* theta, int n, double* lp, double* grad) {
+  if (!data || !theta || !lp || !grad || n < 1) return fail(POTUS_ERR_STATE, "NULL argument");
+  int rc = check_device(0, nullptr);
+  if (rc) return rc;
+  HostModel hm;
+  rc = build_model(data, hm);
+  if (rc) { free_model(hm); return rc; }
+  const int D = hm.m.D;
+  std::vector<float> qin((size_t)n * VEC, 0.f);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < VEC; ++k) {
+      int si = hm.map_i2s[k];
+      if (si >= 0) qin[(size_t)i * VEC + k] = (float)theta[(size_t)i * D + si];
+    }
+  float *dq = nullptr, *dg = nullptr;
+  double* du = nullptr;
+  auto cleanup = [&]() { cudaFree(dq); cudaFree(dg); cudaFree(du); free_model(hm); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&dq, qin.size() * 4)) != cudaSuccess || (e = cudaMalloc(&dg, qin.size() * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&du, (size_t)n * 8)) != cudaSuccess ||
+      (e = cudaMemcpy(dq, qin.data(), qin.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(potus_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES)) != cudaSuccess) {
+    cleanup();
+    return fail(POTUS_ERR_CUDA, cudaGetErrorString(e));
+  }
+  EvalArgs a{};
+  a.m = hm.m; a.n = n; a.q_in = dq; a.g_out = dg; a.u_out = du; a.mu_out = nullptr;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  potus_eval_kernel<<<std::min(n, nsm), NT, SMEM_BYTES>>>(a);
+  std::vector<float> g((size_t)n * VEC);
+  std::vector<double> u(n);
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess || (e = cudaMemcpy(g.data(), dg, g.size() * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+      (e = cudaMemcpy(u.data(), du, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+    cleanup();
+    return fail(POTUS_ERR_CUDA, std::string("potus_eval_kernel: ") + cudaGetErrorString(e));
+  }
+  for (int i = 0; i < n; ++i) {
+    lp[i] = -u[i] + hm.m.lp_const;
+    for (int k = 0; k < VEC; ++k) {
+      int si = hm.map_i2s[k];
+      if (si >= 0) grad[(size_t)i * D + si] = -(double)g[(size_t)i * VEC + k];
+    }
+  }
+  cleanup();
+  return POTUS_OK;
+}
+
+}  // extern "C"

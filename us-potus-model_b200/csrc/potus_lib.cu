@@ -1,0 +1,3 @@
+// Single translation unit of libpotus_b200.so: device kernels + C-ABI host code.
+#include "potus_kernel.cu"
+#include "potus_host.cu"
