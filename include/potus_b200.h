@@ -122,7 +122,8 @@ POTUS_API int potus_get_stats(PotusSampler* s, PotusStats* stats);
  *   which = 0: kept draws   [chains*keep][draw_len]   (draw_len floats per draw, Stan block order:
  *              mu_b | mu_c | mu_m | mu_pop | e_bias | polling_bias | theta)
  *   which = 1: monitor      [chains][iter_sampling][S+1]
- *   which = 2: sampler_params [chains][iter_warmup+iter_sampling][8] */
+ *   which = 2: sampler_params [chains][iter_warmup+iter_sampling][8]  (lp__ and energy__ centred by the
+ *              data constant; potus_get_draws("sampler_params") returns them uncentred in fp64) */
 POTUS_API int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n_floats);
 POTUS_API void potus_destroy(PotusSampler* s);
 POTUS_API const char* potus_last_error(void);

@@ -82,7 +82,7 @@ def logp_literal(theta, data):
     full = is_full_model(data)
     S, T = int(data["S"]), int(data["T"])
     td = transformed_data(data)
-    tt = lambda a: torch.as_tensor(np.asarray(a, float), dtype=dt)
+    tt = lambda a: torch.tensor(np.array(a, dtype=float), dtype=dt)
     w = tt(data["state_weights"])
     # :48-54  three scaled covariances, three Cholesky decompositions (done literally)
     cov0 = tt(data["state_covariance_0"])
@@ -150,7 +150,7 @@ def logp_grad_literal(theta: np.ndarray, data: dict):
     th = torch.tensor(np.asarray(theta, float), dtype=torch.float64, requires_grad=True)
     lp = logp_literal(th, data)
     (g,) = torch.autograd.grad(lp, th)
-    return float(lp), g.numpy()
+    return float(lp.detach()), g.numpy()
 
 
 # ----------------------------------------------------------------------------------------------

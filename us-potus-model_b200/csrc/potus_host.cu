@@ -106,6 +106,21 @@ int validate(const PotusData* d) {
         return fail(POTUS_ERR_INVALID_DATA, buf);
       }
     }
+  {  // positive definite (Stan checks cov_matrix with an LDLT; a failing Cholesky is the same condition)
+    std::vector<double> L((size_t)S * S, 0.0);
+    for (int j = 0; j < S; ++j) {
+      double s = d->state_covariance_0[j + S * j];
+      for (int k = 0; k < j; ++k) s -= L[j * S + k] * L[j * S + k];
+      if (!(s > 0)) return fail(POTUS_ERR_INVALID_DATA, "Exception: poll_model_2020: state_covariance_0 is not positive definite.");
+      double ljj = std::sqrt(s);
+      L[j * S + j] = ljj;
+      for (int i = j + 1; i < S; ++i) {
+        double v = d->state_covariance_0[i + S * j];
+        for (int k = 0; k < j; ++k) v -= L[i * S + k] * L[j * S + k];
+        L[i * S + j] = v / ljj;
+      }
+    }
+  }
   return POTUS_OK;
 }
 
@@ -603,8 +618,14 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   const std::string p = par;
   if (p == "sampler_params") {  // [(iter)*chains, 7], row index = chain*nt + it (draw-fastest within a column)
     const size_t R = (size_t)C * nt;
+    const double c0 = s->hm.m.lp_const;  // device values are centred: lp__ = -U + c0, energy__ = H - c0
     for (size_t r = 0; r < R; ++r)
-      for (int k = 0; k < 7; ++k) out[r + R * k] = s->h_sparams[r * 8 + k];
+      for (int k = 0; k < 7; ++k) {
+        double v = s->h_sparams[r * 8 + k];
+        if (k == 0) v += c0;
+        if (k == 6) v -= c0;
+        out[r + R * k] = v;
+      }
     return POTUS_OK;
   }
   if (p == "monitor") {

@@ -920,7 +920,7 @@ __device__ __noinline__ void transition(const RunArgs& a, const Smem& sm, TC& tc
   global_to_q(m, sm, tc, slot_ptr(ws, samp));
   ptx::tc_fence_before();
   __syncthreads();
-  st.lp = (float)(-U_samp + m.lp_const);
+  st.lp = (float)(-U_samp);  // centred; the host adds lp_const in fp64 (fp32 cannot hold -1.2e6 to 1e-2)
   st.accept = (float)(sum_metro / (double)(n_leap > 0 ? n_leap : 1));
   st.eps = eps; st.depth = (float)depth; st.nleap = (float)n_leap; st.divergent = divergent ? 1.f : 0.f;
   st.energy = (float)H_samp;
