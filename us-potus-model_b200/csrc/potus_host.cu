@@ -280,14 +280,14 @@ int build_model(const PotusData* d, HostModel& hm) {
   prior[NAT_COL] = (float)wp;
 
   // ---- segment-sum tasks
-  std::vector<uint32_t> t1;
+  std::vector<uint2> t1;
   std::vector<uint2> t2;
   std::vector<uint16_t> ids;
   auto add_segments = [&](int type, int start, int cnt, int& pstart, int& pcnt) {
     pstart = (int)t1.size(); pcnt = 0;
     while (cnt > 0) {
       int c = std::min(cnt, 32);
-      t1.push_back((uint32_t)start | ((uint32_t)c << 16) | ((uint32_t)type << 24));
+      t1.push_back(make_uint2((uint32_t)start | ((uint32_t)c << 16) | ((uint32_t)type << 24), (uint32_t)t1.size()));
       start += c; cnt -= c; ++pcnt;
     }
   };
@@ -300,9 +300,8 @@ int build_model(const PotusData* d, HostModel& hm) {
   for (int k = 0; k < N;) {
     int e = k;
     while (e < N && hp[e].dd == hp[k].dd && hp[e].s == hp[k].s && ((e < Ns) == (k < Ns))) ++e;
-    int ps, pc;
-    add_segments(0, k, e - k, ps, pc);
-    add_final(0, hp[k].dd * 64 + hp[k].s, ps, pc);
+    if (e - k > 255) return fail(POTUS_ERR_UNSUPPORTED, "more than 255 polls in one (state, day) cell");
+    add_final(3, hp[k].dd * 64 + hp[k].s, k, e - k);  // direct sum of the cell's residuals
     k = e;
   }
   if (full) {  // g_e[t] = sum over polls of day t of unadjusted * r
@@ -335,6 +334,9 @@ int build_model(const PotusData* d, HostModel& hm) {
       add_final(0, PB_ROW * 64 + s, ps, pc);
     }
   }
+  // balance: longest tasks first, so thread i of every warp gets tasks of similar length
+  std::stable_sort(t1.begin(), t1.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
+  std::stable_sort(t2.begin(), t2.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
   if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || ids.size() > 65535)
     return fail(POTUS_ERR_UNSUPPORTED, "poll structure needs more segment tasks than the resident kernel holds");
   if (seg_overflow) return fail(POTUS_ERR_UNSUPPORTED, "a poll group needs more than 255 segments");
@@ -375,7 +377,7 @@ int build_model(const PotusData* d, HostModel& hm) {
   if ((rc = upload(hm, bt, &p))) return rc; m.btiles = p;
   if ((rc = upload(hm, pk, &p))) return rc; m.pk = (const uint32_t*)p;
   if ((rc = upload(hm, prior, &p))) return rc; m.prior = (const float*)p;
-  if ((rc = upload(hm, t1, &p))) return rc; m.t1 = (const uint32_t*)p;
+  if ((rc = upload(hm, t1, &p))) return rc; m.t1 = (const uint2*)p;
   if ((rc = upload(hm, t2, &p))) return rc; m.t2 = (const uint2*)p;
   if ((rc = upload(hm, ids, &p))) return rc; m.ids = (const uint16_t*)p;
   if ((rc = upload(hm, hm.map_i2s, &p))) return rc; m.map_i2s = (const int32_t*)p;

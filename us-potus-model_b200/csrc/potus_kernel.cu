@@ -6,18 +6,24 @@
 // What it restates (reference file:line; the sampler itself is Stan 2.24.1, not in the tree):
 //   poll_model_2020.stan:70-113  transformed parameters   -> eval_point() forward half
 //   poll_model_2020.stan:115-132 log density               -> eval_point() energy + hand-derived gradient
-//   poll_model_2020.stan:134-140 generated quantities      -> emit_draw()
+//   poll_model_2020.stan:134-140 generated quantities      -> eval_point() emit hooks + host (predicted_score)
 //   Stan base_nuts::transition / build_tree (multinomial NUTS, generalised U-turn with the two
 //   extra sub-tree checks), expl_leapfrog, diag_e_metric, stepsize/var/windowed adaptation,
-//   init_stepsize -> transition(), adapt_*(), find_stepsize().
+//   init_stepsize -> transition(), find_stepsize(), the adaptation block of potus_nuts_kernel.
 // The CPU statement of exactly this algorithm (iterative tree, Philox streams) is
-// oracle/potus_oracle.c (tree_mode 1); tests compare the two.
+// oracle/potus_oracle.c (tree_mode 1); tests compare the two decision by decision.
+//
+// Conventions that keep the hot loops mask-free: every internal vector is zero in its padding
+// slots (walk rows >= T, state columns >= S, nz slots >= NZ), in shared memory, TMEM and global
+// memory alike, so element-wise updates need no validity tests.
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "ptx_sm100.cuh"
 #include "potus_layout.h"
 
 namespace potus {
+
+extern __shared__ __align__(128) unsigned char smem_raw[];
 
 struct Ctl {
   uint64_t bar_mma[2];
@@ -28,61 +34,42 @@ struct Ctl {
   double u_extra;  // -(log-density terms of rho_e_bias)
   float rho, mu_e, sig_rho, rho_term;  // rho_term = sig_e*rho/sqrt(1-rho^2)
   float rn_total;
-  float kred[16];
-  float mred[16][8];
-  int nonfinite;
+  float pad0;
+  alignas(16) float kred[2][16];
+  alignas(16) float mred[16][8];
   ChainState cs;
 };
+static_assert(sizeof(Ctl) <= 1024, "control block");
 
-struct Smem {
-  unsigned char* a;      // operand planes / fp32 scratch
-  unsigned char* b;      // X hi, X lo
-  float* qz;             // [254][52]
-  float* qnz;            // [NZ_CAP]
-  float* gnz;            // [NZ_CAP]
-  uint32_t* pk_idx;
-  float *pk_n, *pk_eta, *pk_p, *pk_rho;
-  float* rr;
-  float* psum;
-  float *e, *ebar;
-  float* tot;
-  float* prior;
-  double* red;
-  Ctl* ctl;
-  float* scr;            // = (float*)a
-};
+#define SMP(T_, off) (reinterpret_cast<T_*>(smem_raw + (off)))
+__device__ __forceinline__ const ModelDev& MD() { return *SMP(const ModelDev, SM_MODEL); }
+__device__ __forceinline__ Ctl& CTL() { return *SMP(Ctl, SM_CTL); }
+__device__ __forceinline__ float* sQZ() { return SMP(float, SM_QZ); }
+__device__ __forceinline__ float* sQNZ() { return SMP(float, SM_QNZ); }
+__device__ __forceinline__ float* sGNZ() { return SMP(float, SM_GNZ); }
+__device__ __forceinline__ float* sSCR() { return SMP(float, SM_A); }
+__device__ __forceinline__ float* sRR() { return SMP(float, SM_RR); }
+__device__ __forceinline__ float* sPSUM() { return SMP(float, SM_PSUM); }
+__device__ __forceinline__ float* sE() { return SMP(float, SM_E); }
+__device__ __forceinline__ float* sEBAR() { return SMP(float, SM_E) + 256; }
+__device__ __forceinline__ float* sTOT() { return SMP(float, SM_TOT); }
+__device__ __forceinline__ float* sPRIOR() { return SMP(float, SM_PRIOR); }
+__device__ __forceinline__ double* sRED() { return SMP(double, SM_RED); }
+__device__ __forceinline__ uint32_t* sPKI() { return SMP(uint32_t, SM_PK); }
+__device__ __forceinline__ float* sPKF(int which) { return SMP(float, SM_PK + which * NPOLL_CAP * 4); }
 
-__device__ __forceinline__ Smem carve(unsigned char* base) {
-  Smem s;
-  s.a = base + SM_A;
-  s.b = base + SM_B;
-  s.qz = reinterpret_cast<float*>(base + SM_QZ);
-  s.qnz = reinterpret_cast<float*>(base + SM_QNZ);
-  s.gnz = reinterpret_cast<float*>(base + SM_GNZ);
-  s.pk_idx = reinterpret_cast<uint32_t*>(base + SM_PK);
-  s.pk_n = reinterpret_cast<float*>(base + SM_PK + 1 * NPOLL_CAP * 4);
-  s.pk_eta = reinterpret_cast<float*>(base + SM_PK + 2 * NPOLL_CAP * 4);
-  s.pk_p = reinterpret_cast<float*>(base + SM_PK + 3 * NPOLL_CAP * 4);
-  s.pk_rho = reinterpret_cast<float*>(base + SM_PK + 4 * NPOLL_CAP * 4);
-  s.rr = reinterpret_cast<float*>(base + SM_RR);
-  s.psum = reinterpret_cast<float*>(base + SM_PSUM);
-  s.e = reinterpret_cast<float*>(base + SM_E);
-  s.ebar = s.e + 256;
-  s.tot = reinterpret_cast<float*>(base + SM_TOT);
-  s.prior = reinterpret_cast<float*>(base + SM_PRIOR);
-  s.red = reinterpret_cast<double*>(base + SM_RED);
-  s.ctl = reinterpret_cast<Ctl*>(base + SM_CTL);
-  s.scr = reinterpret_cast<float*>(base + SM_A);
-  return s;
+// thread-private TMEM window (32 columns) of the calling thread, column offset 0
+__device__ __forceinline__ uint32_t tpriv() {
+  const uint32_t w = threadIdx.x >> 5;
+  return CTL().tmem_base + (((w & 3u) * 32u) << 16) + (w >> 2) * 32u;
 }
-
-struct TC {  // per-thread constants
-  int tid, w, l;
-  bool zlane, nzlane;
-  uint32_t tpriv;  // TMEM address of this thread's private 32-column window (column offset 0)
-  int nz0;         // first nz slot owned (nz lanes)
-  uint32_t ph;     // mbarrier phase parity (both MMA barriers flip once per GEMM)
-};
+// owned position elements come in 16 float2 pairs: pair d of a walk lane = states (2l,2l+1) on day 16w+d;
+// pair d of an nz lane = nz slots nz0+2d, nz0+2d+1.
+__device__ __forceinline__ float2* qpair(int d) {
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  if (l < ZLANES) return reinterpret_cast<float2*>(sQZ() + (16 * w + d) * QZ_PITCH + 2 * l);
+  return reinterpret_cast<float2*>(sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT + 2 * d);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10, same streams as oracle/potus_oracle.c
@@ -113,68 +100,53 @@ __device__ __forceinline__ float rng_normal(unsigned long long seed, uint32_t ch
 // ------------------------------------------------------------------------------------------------
 // thread-private TMEM vectors and owner-layout global vectors (element e of thread tid at [e*512+tid])
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tm_ld16(const TC& tc, uint32_t col, float (&v)[16]) {
-  uint32_t u[16];
-  ptx::tmem_ld16(tc.tpriv + col, u);
+__device__ __forceinline__ void tm_ld16(uint32_t tp, uint32_t col, float (&v)[16]) {
+  ptx::tmem_ld16f(tp + col, v);
   ptx::tmem_wait_ld();
-#pragma unroll
-  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
 }
-__device__ __forceinline__ void tm_st16(const TC& tc, uint32_t col, const float (&v)[16]) {
-  uint32_t u[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(v[j]);
-  ptx::tmem_st16(tc.tpriv + col, u);
-}
+__device__ __forceinline__ void tm_st16(uint32_t tp, uint32_t col, const float (&v)[16]) { ptx::tmem_st16f(tp + col, v); }
 __device__ __forceinline__ float* slot_ptr(float* ws, int slot) { return ws + (size_t)slot * VEC; }
 
-// copy: TMEM private vector <-> global
-__device__ __forceinline__ void tm_to_global(const TC& tc, uint32_t col, float* g) {
+__device__ __forceinline__ void tm_to_global(uint32_t tp, uint32_t col, float* g) {
+  g += threadIdx.x;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
-    tm_ld16(tc, col + 16 * h, v);
+    tm_ld16(tp, col + 16 * h, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) g[(h * 16 + j) * NT + tc.tid] = v[j];
+    for (int j = 0; j < 16; ++j) g[(h * 16 + j) * NT] = v[j];
   }
 }
-__device__ __forceinline__ void global_to_tm(const TC& tc, uint32_t col, const float* g) {
+__device__ __forceinline__ void global_to_tm(uint32_t tp, uint32_t col, const float* g) {
+  g += threadIdx.x;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = g[(h * 16 + j) * NT + tc.tid];
-    tm_st16(tc, col + 16 * h, v);
+    for (int j = 0; j < 16; ++j) v[j] = g[(h * 16 + j) * NT];
+    tm_st16(tp, col + 16 * h, v);
   }
   ptx::tmem_wait_st();
 }
-// position element access in shared memory for owned element e
-__device__ __forceinline__ float* q_elem(const Smem& sm, const TC& tc, int e) {
-  if (tc.zlane) return sm.qz + (16 * tc.w + (e >> 1)) * QZ_PITCH + 2 * tc.l + (e & 1);
-  return sm.qnz + tc.nz0 + e;
-}
-// is owned element e a real parameter (not padding)?
-__device__ __forceinline__ bool elem_valid(const ModelDev& m, const TC& tc, int e) {
-  if (tc.zlane) return (16 * tc.w + (e >> 1)) < m.T && (2 * tc.l + (e & 1)) < m.S;
-  if (tc.nzlane) return tc.nz0 + e < m.NZ;
-  return false;
-}
-__device__ __forceinline__ void q_to_global(const ModelDev& m, const Smem& sm, const TC& tc, float* g) {
+__device__ __forceinline__ void q_to_global(float* g) {
+  g += threadIdx.x;
 #pragma unroll
-  for (int e = 0; e < EPT; ++e) g[e * NT + tc.tid] = elem_valid(m, tc, e) ? *q_elem(sm, tc, e) : 0.0f;
-}
-__device__ __forceinline__ void global_to_q(const ModelDev& m, const Smem& sm, const TC& tc, const float* g) {
-#pragma unroll
-  for (int e = 0; e < EPT; ++e) {
-    float v = g[e * NT + tc.tid];
-    if (elem_valid(m, tc, e)) *q_elem(sm, tc, e) = v;
+  for (int d = 0; d < 16; ++d) {
+    const float2 v = *qpair(d);
+    g[(2 * d) * NT] = v.x;
+    g[(2 * d + 1) * NT] = v.y;
   }
 }
+__device__ __forceinline__ void global_to_q(const float* g) {
+  g += threadIdx.x;
+  float2 v[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) { v[d].x = g[(2 * d) * NT]; v[d].y = g[(2 * d + 1) * NT]; }
+#pragma unroll
+  for (int d = 0; d < 16; ++d) *qpair(d) = v[d];
+}
 
-// ------------------------------------------------------------------------------------------------
-// affine-map warp scan helpers (AR(1) recurrences)
-// ------------------------------------------------------------------------------------------------
-// inclusive scan of maps x -> A x + B, composition "later after earlier"; lane order ascending
+// inclusive scan of affine maps x -> A x + B over the lanes of a warp (AR(1) recurrences)
 __device__ __forceinline__ void affine_scan(float& A, float& B, int l) {
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -183,38 +155,52 @@ __device__ __forceinline__ void affine_scan(float& A, float& B, int l) {
   }
 }
 
-
 // Accumulator read-out shared by both GEMMs: (D1 + D2/2048) * scale (+ prior for day rows) -> fp32
 // scratch [row][53].  The scratch aliases the operand planes, so nothing is written before the LAST
 // commit (bar_mma[1]) has completed; tile-0 warps still overlap their TMEM loads with tile 1's MMAs.
-__device__ __forceinline__ void tmem_epilogue(const ModelDev& m, const Smem& sm, const TC& tc, float scale, bool add_prior) {
-  Ctl* ctl = sm.ctl;
-  const int w = tc.w, l = tc.l, T = m.T;
+__device__ __forceinline__ void tmem_epilogue(float scale, bool add_prior, uint32_t parity) {
+  Ctl& ctl = CTL();
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31, T = MD().T;
   const int g = w >> 2, tile = g >> 1, half = g & 1, qd = w & 3;
-  ptx::mbar_wait(&ctl->bar_mma[tile], tc.ph);
+  ptx::mbar_wait(&ctl.bar_mma[tile], parity);
   ptx::tc_fence_after();
   const int row = tile * 128 + qd * 32 + l;
-  const uint32_t taddr = ctl->tmem_base + ((uint32_t)(qd * 32) << 16) + tile * 64 + half * 32;
+  const uint32_t taddr = ctl.tmem_base + ((uint32_t)(qd * 32) << 16) + tile * 64 + half * 32;
   const bool rowok = (row < T) || (row == PB_ROW);
-  uint32_t d1[16], d2[16];
-  ptx::tmem_ld16(taddr + TM_D1, d1);
-  ptx::tmem_ld16(taddr + TM_D2, d2);
+  const bool prior_row = add_prior && row < T;
+  float* out = sSCR() + row * SCR_PITCH + half * 32;
+  const float* pr = sPRIOR() + half * 32;
+  float d1[16], d2[16];
+  ptx::tmem_ld16f(taddr + TM_D1, d1);
+  ptx::tmem_ld16f(taddr + TM_D2, d2);
   ptx::tmem_wait_ld();
-  if (tile == 0) ptx::mbar_wait(&ctl->bar_mma[1], tc.ph);
-#pragma unroll
-  for (int cc = 0; cc < 2; ++cc) {
-    if (cc == 1) {
-      ptx::tmem_ld16(taddr + TM_D1 + 16, d1);
-      ptx::tmem_ld16(taddr + TM_D2 + 16, d2);
-      ptx::tmem_wait_ld();
-    }
+  if (tile == 0) ptx::mbar_wait(&ctl.bar_mma[1], parity);
+  if (rowok) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int col = half * 32 + cc * 16 + j;
-      if (col < 52 && rowok) {
-        float v = (__uint_as_float(d1[j]) + __uint_as_float(d2[j]) * (1.0f / 2048.0f)) * scale;
-        if (add_prior && row < T) v += sm.prior[col];
-        sm.scr[row * SCR_PITCH + col] = v;
+      float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
+      if (prior_row) v += pr[j];
+      out[j] = v;
+    }
+  }
+  // second 16 columns: half 0 -> cols 16..31, half 1 -> cols 48..63 of which only 48..51 exist
+  ptx::tmem_ld16f(taddr + TM_D1 + 16, d1);
+  ptx::tmem_ld16f(taddr + TM_D2 + 16, d2);
+  ptx::tmem_wait_ld();
+  if (rowok) {
+    if (half == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
+        if (prior_row) v += pr[16 + j];
+        out[16 + j] = v;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
+        if (prior_row) v += pr[16 + j];
+        out[16 + j] = v;
       }
     }
   }
@@ -227,303 +213,333 @@ struct Emit {
   float* mu;       // [S*T] or null (test hook)
 };
 
+// issue one split-precision GEMM: D1 = A_hi B_hi ; D2 = A_hi B_lo + A_lo B_hi   (2 M-tiles, K = 64)
+__device__ __forceinline__ void issue_gemm(bool b_mn_major) {
+  Ctl& ctl = CTL();
+  ptx::tc_fence_after();
+  const uint32_t idesc = ptx::make_idesc_f16(128, 64, 0, b_mn_major ? 1 : 0);
+  const uint32_t a0 = ptx::smem_u32(smem_raw + SM_A), b0 = ptx::smem_u32(smem_raw + SM_B), tb = ctl.tmem_base;
+#pragma unroll
+  for (int tile = 0; tile < 2; ++tile) {
+#pragma unroll
+    for (int prod = 0; prod < 3; ++prod) {
+      const uint32_t ap = a0 + (prod == 2 ? A_PLANE : 0) + tile * 16 * A_SBO;
+      const uint32_t bp = b0 + (prod == 1 ? B_PLANE : 0);
+      const uint32_t dcol = tb + tile * 64 + (prod == 0 ? TM_D1 : TM_D2);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint64_t ad = ptx::make_smem_desc(ap + ks * 2 * A_LBO, A_LBO, A_SBO);
+        const uint64_t bd = b_mn_major ? ptx::make_smem_desc(bp + ks * 2 * B_SBO, /*LBO: k groups*/ B_SBO, /*SBO: n groups*/ B_LBO)
+                                       : ptx::make_smem_desc(bp + ks * 2 * B_LBO, B_LBO, B_SBO);
+        ptx::mma_f16_ss(dcol, ad, bd, idesc, (prod == 2) ? 1u : (uint32_t)(ks > 0));
+      }
+    }
+    ptx::mma_commit(&ctl.bar_mma[tile]);
+  }
+}
+
 // ================================================================================================
-// eval_point: potential U (-> ctl->U) and its gradient (-> TMEM TM_G, owner layout) at the position
-// held in shared memory.  Must be called by all 512 threads.
+// eval_point: potential U (-> ctl.U) and its gradient (-> TMEM TM_G, owner layout) at the position
+// held in shared memory.  Called by all 512 threads.  Both mbarriers complete exactly twice per call,
+// so their phase parity is 0 for GEMM 1 and 1 for GEMM 2 on every call.
 // ================================================================================================
-__device__ __noinline__ void eval_point(const ModelDev& m, const Smem& sm, TC& tc, const Emit em) {
-  const int T = m.T, S = m.S, w = tc.w, l = tc.l, tid = tc.tid;
-  Ctl* ctl = sm.ctl;
-  float qsq = 0.f;  // sum of squares of owned parameters (prior energy)
+__device__ __noinline__ void eval_point(const Emit em) {
+  const ModelDev& m = MD();
+  Ctl& ctl = CTL();
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  const int T = m.T, S = m.S;
+  const bool zlane = l < ZLANES;
+  const int nd = min(max(T - 16 * w, 0), 16);       // day rows of this warp that exist
+  const int ndw = min(max(T - 1 - 16 * w, 0), 16);  // ... that carry a walk innovation (t <= T-2)
+  float qsq = 0.f;
 
   // ---------------- P1: reverse scan of the walk innovations (poll_model_2020.stan:86 collapsed)
   float c[32];
-  {
+  if (zlane) {
     float run0 = 0.f, run1 = 0.f;
-    if (tc.zlane) {
+    const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
 #pragma unroll
-      for (int d = 15; d >= 0; --d) {
-        const int t = 16 * w + d;
-        float2 z = make_float2(0.f, 0.f);
-        if (t < T) z = *reinterpret_cast<const float2*>(sm.qz + t * QZ_PITCH + 2 * l);
-        qsq += z.x * z.x + z.y * z.y;
-        if (t <= T - 2) { run0 += z.x; run1 += z.y; }
-        c[2 * d] = run0; c[2 * d + 1] = run1;
-      }
-      sm.tot[w * 52 + 2 * l] = run0;
-      sm.tot[w * 52 + 2 * l + 1] = run1;
-    } else if (tc.nzlane) {
+    for (int d = 15; d >= 0; --d) {
+      const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
+      qsq = fmaf(z.x, z.x, fmaf(z.y, z.y, qsq));
+      if (d < ndw) { run0 += z.x; run1 += z.y; }
+      c[2 * d] = run0; c[2 * d + 1] = run1;
+    }
+    *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
+  } else {
+    const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) { float v = sm.qnz[tc.nz0 + e]; qsq += v * v; }
-      if (m.full) {  // rho's unconstrained value carries no N(0,1) term
-        int k = m.nz_urho - tc.nz0;
-        if (k >= 0 && k < EPT) { float v = sm.qnz[m.nz_urho]; qsq -= v * v; }
-      }
+    for (int e = 0; e < EPT; e += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(qn + e);
+      qsq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (m.full) {  // rho's unconstrained value carries no N(0,1) term
+      const int k = m.nz_urho - (w * NZ_LANES + (l - ZLANES)) * EPT;
+      if (k >= 0 && k < EPT) { const float v = sQNZ()[m.nz_urho]; qsq -= v * v; }
     }
   }
   __syncthreads();  // S1
   // ---------------- P2: W -> fp16 hi/lo operand planes (K-major, SWIZZLE_NONE)
   {
     float carry0 = 0.f, carry1 = 0.f, zt0 = 0.f, zt1 = 0.f, zb0 = 0.f, zb1 = 0.f;
-    const bool act = tc.zlane && l < m.npair;
+    const bool act = l < m.npair;
     if (act) {
-      for (int w2 = w + 1; w2 < NWARP; ++w2) { carry0 += sm.tot[w2 * 52 + 2 * l]; carry1 += sm.tot[w2 * 52 + 2 * l + 1]; }
-      zt0 = sm.qnz[m.nz_zT + 2 * l]; zb0 = sm.qnz[m.nz_zb + 2 * l];
-      if (2 * l + 1 < S) { zt1 = sm.qnz[m.nz_zT + 2 * l + 1]; zb1 = sm.qnz[m.nz_zb + 2 * l + 1]; }
+      for (int w2 = w + 1; w2 < NWARP; ++w2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(sTOT() + w2 * 52 + 2 * l);
+        carry0 += t2.x; carry1 += t2.y;
+      }
+      zt0 = sQNZ()[m.nz_zT + 2 * l];
+      zb0 = sQNZ()[m.nz_zb + 2 * l];
+      if (2 * l + 1 < S) { zt1 = sQNZ()[m.nz_zT + 2 * l + 1]; zb1 = sQNZ()[m.nz_zb + 2 * l + 1]; }
     }
-    const uint32_t colofs = (uint32_t)(l >> 2) * A_LBO + (uint32_t)(l & 3) * 4;
+    const float base0 = m.a_T * zt0 + m.a_w * carry0, base1 = m.a_T * zt1 + m.a_w * carry1;
+    unsigned char* ap = smem_raw + SM_A + (uint32_t)(l >> 2) * A_LBO + (uint32_t)(l & 3) * 4 + (uint32_t)(2 * w) * A_SBO;
 #pragma unroll
     for (int d = 0; d < 16; ++d) {
-      const int t = 16 * w + d;
       float v0 = 0.f, v1 = 0.f;
       if (act) {
-        if (t < T) { v0 = m.a_T * zt0 + m.a_w * (c[2 * d] + carry0); v1 = m.a_T * zt1 + m.a_w * (c[2 * d + 1] + carry1); }
-        else if (t == PB_ROW) { v0 = m.a_b * zb0; v1 = m.a_b * zb1; }
+        if (d < nd) { v0 = fmaf(m.a_w, c[2 * d], base0); v1 = fmaf(m.a_w, c[2 * d + 1], base1); }
+        else if (16 * w + d == PB_ROW) { v0 = m.a_b * zb0; v1 = m.a_b * zb1; }
         if (2 * l + 1 >= S) v1 = 0.f;
       }
-      __half h0, l0, h1, l1;
-      ptx::split_f16(v0, h0, l0);
-      ptx::split_f16(v1, h1, l1);
-      const uint32_t off = colofs + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16;
-      *reinterpret_cast<__half2*>(sm.a + off) = __halves2half2(h0, h1);
-      *reinterpret_cast<__half2*>(sm.a + A_PLANE + off) = __halves2half2(l0, l1);
+      const __half2 hi = __floats2half2_rn(v0, v1);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __floats2half2_rn((v0 - hf.x) * 2048.0f, (v1 - hf.y) * 2048.0f);
+      const uint32_t off = (uint32_t)(d >> 3) * A_SBO + (uint32_t)(d & 7) * 16;
+      *reinterpret_cast<__half2*>(ap + off) = hi;
+      *reinterpret_cast<__half2*>(ap + A_PLANE + off) = lo;
     }
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();  // S2
-  // ---------------- P3: mu_b^T = W^T X^T on the tensor core (2 M-tiles x 3 split products x 4 K-steps)
-  if (tid == 0) {
-    ptx::tc_fence_after();
-    const uint32_t idesc = ptx::make_idesc_f16(128, 64, 0, 0);
-    const uint32_t a0 = ptx::smem_u32(sm.a), b0 = ptx::smem_u32(sm.b), tb = ctl->tmem_base;
-    for (int tile = 0; tile < 2; ++tile) {
-#pragma unroll
-      for (int prod = 0; prod < 3; ++prod) {
-        const uint32_t ap = a0 + (prod == 2 ? A_PLANE : 0) + tile * 16 * A_SBO;
-        const uint32_t bp = b0 + (prod == 1 ? B_PLANE : 0);
-        const uint32_t dcol = tb + tile * 64 + (prod == 0 ? TM_D1 : TM_D2);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint64_t ad = ptx::make_smem_desc(ap + ks * 2 * A_LBO, A_LBO, A_SBO);
-          uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * B_LBO, B_LBO, B_SBO);
-          ptx::mma_f16_ss(dcol, ad, bd, idesc, (prod == 2) ? 1u : (ks > 0));
-        }
-      }
-      ptx::mma_commit(&ctl->bar_mma[tile]);
-    }
-  }
+  // ---------------- P3: mu_b^T = W^T X^T on the tensor core
+  if (tid == 0) issue_gemm(false);
   // overlapped with the MMA: AR(1) partisan non-response bias, poll_model_2020.stan:91-93 (warp 1)
-  if (m.full && w == 1) {
-    const float u_rho = sm.qnz[m.nz_urho], u_mu = sm.qnz[m.nz_umu];
-    const float rho = 1.0f / (1.0f + __expf(-u_rho));
-    const float mu_e = 0.02f * u_mu;
-    const float s2 = sqrtf(fmaxf(1.0f - rho * rho, 0.f));
-    const float sig_rho = s2 * m.sig_e;
-    const float cst = mu_e * (1.0f - rho);
-    float A = 1.f, B = 0.f;
-    float u[8];
+  if (w == 1) {
+    if (m.full) {
+      const float* ze = sQNZ() + m.nz_ze;
+      const float u_rho = sQNZ()[m.nz_urho], u_mu = sQNZ()[m.nz_umu];
+      const float rho = 1.0f / (1.0f + __expf(-u_rho));
+      const float mu_e = 0.02f * u_mu;
+      const float s2 = sqrtf(fmaxf(1.0f - rho * rho, 0.f));
+      const float sig_rho = s2 * m.sig_e;
+      const float cst = mu_e * (1.0f - rho);
+      float A = 1.f, B = 0.f;
+      float u[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int t = 8 * l + j;
-      float uj = 0.f, aj = 1.f;
-      if (t < T) { aj = rho; uj = (t == 0) ? m.sig_e * sm.qnz[m.nz_ze] : cst + sig_rho * sm.qnz[m.nz_ze + t]; }
-      u[j] = uj;
-      B = aj * B + uj; A = aj * A;
-    }
-    affine_scan(A, B, l);
-    float ein = __shfl_up_sync(0xffffffffu, B, 1);
-    if (l == 0) ein = 0.f;
+      for (int j = 0; j < 8; ++j) {
+        const int t = 8 * l + j;
+        float uj = 0.f, aj = 1.f;
+        if (t < T) { aj = rho; uj = (t == 0) ? m.sig_e * ze[0] : cst + sig_rho * ze[t]; }
+        u[j] = uj;
+        B = aj * B + uj; A = aj * A;
+      }
+      affine_scan(A, B, l);
+      float ein = __shfl_up_sync(0xffffffffu, B, 1);
+      if (l == 0) ein = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int t = 8 * l + j;
-      if (t < T) { ein = rho * ein + u[j]; sm.e[t] = ein; }
-    }
-    if (l == 0) {
-      ctl->rho = rho; ctl->mu_e = mu_e; ctl->sig_rho = sig_rho; ctl->rho_term = m.sig_e * rho / fmaxf(s2, 1e-20f);
-      // -(normal(0.7,0.1) prior + log-Jacobian of the (0,1) transform), fp64
-      const double r = 1.0 / (1.0 + exp(-(double)u_rho));
-      ctl->u_extra = 0.5 * ((r - 0.7) / 0.1) * ((r - 0.7) / 0.1) - log(r) - log1p(-r);
+      for (int j = 0; j < 8; ++j) {
+        const int t = 8 * l + j;
+        if (t < T) { ein = rho * ein + u[j]; sE()[t] = ein; }
+      }
+      if (l == 0) {
+        ctl.rho = rho; ctl.mu_e = mu_e; ctl.sig_rho = sig_rho; ctl.rho_term = m.sig_e * rho / fmaxf(s2, 1e-20f);
+        // -(normal(0.7,0.1) prior + log-Jacobian of the (0,1) transform), fp64
+        const double r = 1.0 / (1.0 + exp(-(double)u_rho));
+        ctl.u_extra = 0.5 * ((r - 0.7) / 0.1) * ((r - 0.7) / 0.1) - log(r) - log1p(-r);
+      }
+    } else if (l == 0) {
+      ctl.u_extra = 0.0;
     }
   }
-  if (!m.full && tid == 32) ctl->u_extra = 0.0;
   // ---------------- P4: epilogue 1: TMEM -> mu_b (+prior) in the fp32 scratch
-  tmem_epilogue(m, sm, tc, (1.0f / 256.0f), true);
+  tmem_epilogue(1.0f / 256.0f, true, 0);
   __syncthreads();  // S3
   // ---------------- optional outputs (transformed parameters / generated quantities of this point)
   if (em.draw != nullptr) {
     float* o = em.draw;
-    for (int i = tid; i < S * T; i += NT) { int t = i / S, s = i - t * S; o[i] = sm.scr[t * SCR_PITCH + s]; }
+    for (int i = tid; i < S * T; i += NT) { int t = i / S, s = i - t * S; o[i] = sSCR()[t * SCR_PITCH + s]; }
     o += S * T;
-    for (int i = tid; i < m.P; i += NT) o[i] = m.sig_c * sm.qnz[m.nz_c + i];
+    for (int i = tid; i < m.P; i += NT) o[i] = m.sig_c * sQNZ()[m.nz_c + i];
     o += m.P;
-    for (int i = tid; i < m.M; i += NT) o[i] = m.full ? m.sig_m * sm.qnz[m.nz_m + i] : 0.f;
+    for (int i = tid; i < m.M; i += NT) o[i] = m.full ? m.sig_m * sQNZ()[m.nz_m + i] : 0.f;
     o += m.M;
-    for (int i = tid; i < m.Pop; i += NT) o[i] = m.full ? m.sig_pop * sm.qnz[m.nz_pop + i] : 0.f;
+    for (int i = tid; i < m.Pop; i += NT) o[i] = m.full ? m.sig_pop * sQNZ()[m.nz_pop + i] : 0.f;
     o += m.Pop;
-    for (int i = tid; i < T; i += NT) o[i] = m.full ? sm.e[i] : 0.f;
+    for (int i = tid; i < T; i += NT) o[i] = m.full ? sE()[i] : 0.f;
     o += T;
-    for (int i = tid; i < S; i += NT) o[i] = sm.scr[PB_ROW * SCR_PITCH + i];
+    for (int i = tid; i < S; i += NT) o[i] = sSCR()[PB_ROW * SCR_PITCH + i];
     o += S;
 #pragma unroll 4
-    for (int e = 0; e < EPT; ++e) {
-      int si = m.map_i2s[e * NT + tid];
-      if (si >= 0) o[si] = *q_elem(sm, tc, e);
+    for (int d = 0; d < 16; ++d) {
+      const float2 v = *qpair(d);
+      const int s0 = m.map_i2s[(2 * d) * NT + tid], s1 = m.map_i2s[(2 * d + 1) * NT + tid];
+      if (s0 >= 0) o[s0] = v.x;
+      if (s1 >= 0) o[s1] = v.y;
     }
   }
   if (em.monitor != nullptr) {
-    for (int i = tid; i < S; i += NT) em.monitor[i] = sm.scr[(T - 1) * SCR_PITCH + i];
-    if (tid == 0) em.monitor[S] = sm.scr[(T - 1) * SCR_PITCH + NAT_COL];
+    for (int i = tid; i < S; i += NT) em.monitor[i] = sSCR()[(T - 1) * SCR_PITCH + i];
+    if (tid == 0) em.monitor[S] = sSCR()[(T - 1) * SCR_PITCH + NAT_COL];
   }
   if (em.mu != nullptr)
-    for (int i = tid; i < S * T; i += NT) { int t = i / S, s = i - t * S; em.mu[i] = sm.scr[t * SCR_PITCH + s]; }
+    for (int i = tid; i < S * T; i += NT) { int t = i / S, s = i - t * S; em.mu[i] = sSCR()[t * SCR_PITCH + s]; }
 
   // ---------------- P5: polls: linear predictor (stan:95-112), centred binomial_logit (stan:130-131), residuals
-  float fsum = 0.f, gm[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, gp[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, rnat = 0.f;
-  for (int k = tid; k < m.N; k += NT) {
-    const uint32_t ix = sm.pk_idx[k];
-    const int s = ix & 63, d = (ix >> 6) & 255, p = (ix >> 14) & 1023, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
-    const float un = (float)((ix >> 30) & 1);
-    const bool nat = (s == NAT_COL);
-    const float sigx = nat ? m.sig_n : m.sig_s;
-    float eta = sm.scr[d * SCR_PITCH + s] + sm.scr[PB_ROW * SCR_PITCH + s] + m.sig_c * sm.qnz[m.nz_c + p] +
-                sigx * sm.qnz[m.nz_x + k];
-    if (m.full) eta += m.sig_m * sm.qnz[m.nz_m + mo] + m.sig_pop * sm.qnz[m.nz_pop + po] + un * sm.e[d];
-    const float n = sm.pk_n[k], eh = sm.pk_eta[k], ph = sm.pk_p[k], rh = sm.pk_rho[k];
-    const float dl = eta - eh;
-    float f, r;
-    if (fabsf(dl) < 12.0f) {
-      // ll(eta) - ll(eta_hat) = n [ (y/n) dl - log1p(p_hat expm1(dl)) ],  y/n = p_hat + rho_hat
-      const float em1 = expm1f(dl);
-      const float uu = ph * em1;
-      f = n * (rh * dl + (ph * dl - log1pf(uu)));
-      r = n * (rh - ph * (1.0f - ph) * em1 / (1.0f + uu));
-    } else {  // far tail: direct, stable softplus difference (accuracy irrelevant out here)
-      const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
-      const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
-      const float sg = 1.0f / (1.0f + __expf(-eta));
-      f = n * ((ph + rh) * dl - (sp - sph));
-      r = n * ((ph + rh) - sg);
-    }
-    fsum += f;
-    sm.rr[k] = r;
-    sm.gnz[m.nz_x + k] = sigx * r;
-    if (nat) rnat += r;
-    if (m.full) {
-#pragma unroll
-      for (int j = 0; j < MAX_MODE; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
-    }
-  }
   {
-    double v[10];
-    v[0] = 0.5 * (double)qsq - (double)fsum;
-    v[1] = (double)rnat;
+    float fsum = 0.f, gm[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, gp[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, rnat = 0.f;
+    const float* scr = sSCR();
+    const float* qn = sQNZ();
+    const float* pbrow = scr + PB_ROW * SCR_PITCH;
+    const bool full = m.full;
+    for (int k = tid; k < m.N; k += NT) {
+      const uint32_t ix = sPKI()[k];
+      const int s = ix & 63, d = (ix >> 6) & 255, p = (ix >> 14) & 1023, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
+      const bool nat = (s == NAT_COL);
+      const float sigx = nat ? m.sig_n : m.sig_s;
+      float eta = scr[d * SCR_PITCH + s] + pbrow[s] + m.sig_c * qn[m.nz_c + p] + sigx * qn[m.nz_x + k];
+      if (full) {
+        eta += m.sig_m * qn[m.nz_m + mo] + m.sig_pop * qn[m.nz_pop + po];
+        if ((ix >> 30) & 1) eta += sE()[d];
+      }
+      const float n = sPKF(1)[k], eh = sPKF(2)[k], ph = sPKF(3)[k], rh = sPKF(4)[k];
+      const float dl = eta - eh;
+      float f, r;
+      if (fabsf(dl) < 12.0f) {
+        // ll(eta) - ll(eta_hat) = n [ (y/n) dl - log1p(p_hat expm1(dl)) ],  y/n = p_hat + rho_hat
+        const float em1 = expm1f(dl);
+        const float uu = ph * em1;
+        f = n * (rh * dl + (ph * dl - log1pf(uu)));
+        r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
+      } else {  // far tail: direct, stable softplus difference (accuracy irrelevant out here)
+        const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
+        const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
+        const float sg = 1.0f / (1.0f + __expf(-eta));
+        f = n * ((ph + rh) * dl - (sp - sph));
+        r = n * ((ph + rh) - sg);
+      }
+      fsum += f;
+      sRR()[k] = r;
+      sGNZ()[m.nz_x + k] = sigx * r;
+      if (nat) rnat += r;
+      if (full) {
 #pragma unroll
-    for (int j = 0; j < MAX_MODE; ++j) { v[2 + j] = (double)gm[j]; v[6 + j] = (double)gp[j]; }
+        for (int j = 0; j < MAX_MODE; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
+      }
+    }
+    double v0 = 0.5 * (double)qsq - (double)fsum;
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int off = 16; off > 0; off >>= 1) {
+      v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+      rnat += __shfl_xor_sync(0xffffffffu, rnat, off);
+    }
+    if (full) {
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+      for (int j = 0; j < MAX_MODE; ++j) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          gm[j] += __shfl_xor_sync(0xffffffffu, gm[j], off);
+          gp[j] += __shfl_xor_sync(0xffffffffu, gp[j], off);
+        }
+      }
     }
     if (l == 0) {
+      double* red = sRED() + w * 12;
+      red[0] = v0; red[1] = (double)rnat;
 #pragma unroll
-      for (int i = 0; i < 10; ++i) sm.red[w * 12 + i] = v[i];
+      for (int j = 0; j < MAX_MODE; ++j) { red[2 + j] = (double)gm[j]; red[6 + j] = (double)gp[j]; }
     }
   }
   __syncthreads();  // S4
   // ---------------- P6: level-1 segment sums of residuals (cells, days, pollsters, states)
-  for (int i = tid; i < m.n_t1; i += NT) {
-    const uint32_t td = __ldg(m.t1 + i);
-    const int start = td & 0xffff, cnt = (td >> 16) & 0xff, type = td >> 24;
-    float acc = 0.f;
-    if (type == 0) {
-      for (int j = 0; j < cnt; ++j) acc += sm.rr[start + j];
-    } else if (type == 1) {
-      for (int j = 0; j < cnt; ++j) acc += ((sm.pk_idx[start + j] >> 30) & 1) ? sm.rr[start + j] : 0.f;
-    } else {
-      for (int j = 0; j < cnt; ++j) acc += sm.rr[__ldg(m.ids + start + j)];
+  {
+    const float* rr = sRR();
+    for (int i = tid; i < m.n_t1; i += NT) {
+      const uint2 tdd = __ldg(m.t1 + i);
+      const uint32_t td = tdd.x;
+      const int start = td & 0xffff, cnt = (td >> 16) & 0xff, type = td >> 24;
+      float acc = 0.f;
+      if (type == 0) {
+        for (int j = 0; j < cnt; ++j) acc += rr[start + j];
+      } else if (type == 1) {
+        for (int j = 0; j < cnt; ++j) acc += ((sPKI()[start + j] >> 30) & 1) ? rr[start + j] : 0.f;
+      } else {
+        const uint16_t* ids = m.ids + start;
+        for (int j = 0; j < cnt; ++j) acc += rr[__ldg(ids + j)];
+      }
+      sPSUM()[tdd.y] = acc;
     }
-    sm.psum[i] = acc;
   }
   if (w == 0 && l < 10) {  // finalize the block reduction
     double s = 0;
-    for (int w2 = 0; w2 < NWARP; ++w2) s += sm.red[w2 * 12 + l];
-    if (l == 0) ctl->U = s;  // u_extra added below (written by warp 1 before S3)
-    else if (l == 1) ctl->rn_total = (float)s;
+#pragma unroll
+    for (int w2 = 0; w2 < NWARP; ++w2) s += sRED()[w2 * 12 + l];
+    if (l == 0) ctl.U = s + ctl.u_extra;
+    else if (l == 1) ctl.rn_total = (float)s;
     else if (m.full) {
-      if (l < 2 + MAX_MODE) { if (l - 2 < m.M) sm.gnz[m.nz_m + l - 2] = m.sig_m * (float)s; }
-      else if (l - 6 < m.Pop) sm.gnz[m.nz_pop + l - 6] = m.sig_pop * (float)s;
+      if (l < 2 + MAX_MODE) { if (l - 2 < m.M) sGNZ()[m.nz_m + l - 2] = m.sig_m * (float)s; }
+      else if (l - 6 < m.Pop) sGNZ()[m.nz_pop + l - 6] = m.sig_pop * (float)s;
     }
   }
   // zero the operand planes (scratch reads finished at S4)
   {
-    uint4* a4 = reinterpret_cast<uint4*>(sm.a);
+    uint4* a4 = SMP(uint4, SM_A);
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < (int)(A_REGION / 16); i += NT) a4[i] = z;
+#pragma unroll
+    for (int i = 0; i < (int)(A_REGION / 16 + NT - 1) / NT; ++i) {
+      const int k = tid + i * NT;
+      if (k < (int)(A_REGION / 16)) a4[k] = z;
+    }
   }
   __syncthreads();  // S5
   // ---------------- P7: level-2 finals -> G operand cells / pollster gradients / g_e
-  for (int i = tid; i < m.n_t2; i += NT) {
-    const uint2 td = __ldg(m.t2 + i);
-    const int ps = td.x & 0xffff, pc = (td.x >> 16) & 0xff, kind = td.x >> 24;
-    float acc = 0.f;
-    for (int j = 0; j < pc; ++j) acc += sm.psum[ps + j];
-    if (kind == 0) {
-      const int t = td.y >> 6, s = td.y & 63;
-      __half hi, lo;
-      ptx::split_f16(acc * m.scale_G, hi, lo);
-      const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
-      *reinterpret_cast<__half*>(sm.a + off) = hi;
-      *reinterpret_cast<__half*>(sm.a + A_PLANE + off) = lo;
-    } else if (kind == 1) {
-      sm.gnz[td.y] = m.sig_c * acc;
-    } else {
-      sm.ebar[td.y] = acc;
+  {
+    const float* ps_ = sPSUM();
+    for (int i = tid; i < m.n_t2; i += NT) {
+      const uint2 td = __ldg(m.t2 + i);
+      const int ps = td.x & 0xffff, pc = (td.x >> 16) & 0xff, kind = td.x >> 24;
+      const float* src = (kind == 3) ? sRR() : ps_;
+      float acc = 0.f;
+      for (int j = 0; j < pc; ++j) acc += src[ps + j];
+      if (kind == 0 || kind == 3) {
+        const int t = td.y >> 6, s = td.y & 63;
+        __half hi, lo;
+        ptx::split_f16(acc * m.scale_G, hi, lo);
+        const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
+        *reinterpret_cast<__half*>(smem_raw + SM_A + off) = hi;
+        *reinterpret_cast<__half*>(smem_raw + SM_A + A_PLANE + off) = lo;
+      } else if (kind == 1) {
+        sGNZ()[td.y] = m.sig_c * acc;
+      } else {
+        sEBAR()[td.y] = acc;
+      }
     }
-  }
-  if (tid == 0) {  // polling-bias row, national K-slot: sum of all national residuals
-    __half hi, lo;
-    ptx::split_f16(ctl->rn_total * m.scale_G, hi, lo);
-    const int t = PB_ROW, s = NAT_COL;
-    const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
-    *reinterpret_cast<__half*>(sm.a + off) = hi;
-    *reinterpret_cast<__half*>(sm.a + A_PLANE + off) = lo;
-    ctl->U += ctl->u_extra;
+    if (tid == 0) {  // polling-bias row, national K-slot: sum of all national residuals
+      __half hi, lo;
+      ptx::split_f16(ctl.rn_total * m.scale_G, hi, lo);
+      const int t = PB_ROW, s = NAT_COL;
+      const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
+      *reinterpret_cast<__half*>(smem_raw + SM_A + off) = hi;
+      *reinterpret_cast<__half*>(smem_raw + SM_A + A_PLANE + off) = lo;
+    }
   }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();  // S6
   // ---------------- P8: H^T = G^T X  (B consumed MN-major: the same X planes, transposed view)
-  if (tid == 0) {
-    ptx::tc_fence_after();
-    const uint32_t idesc = ptx::make_idesc_f16(128, 64, 0, 1);
-    const uint32_t a0 = ptx::smem_u32(sm.a), b0 = ptx::smem_u32(sm.b), tb = ctl->tmem_base;
-    for (int tile = 0; tile < 2; ++tile) {
-#pragma unroll
-      for (int prod = 0; prod < 3; ++prod) {
-        const uint32_t ap = a0 + (prod == 2 ? A_PLANE : 0) + tile * 16 * A_SBO;
-        const uint32_t bp = b0 + (prod == 1 ? B_PLANE : 0);
-        const uint32_t dcol = tb + tile * 64 + (prod == 0 ? TM_D1 : TM_D2);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint64_t ad = ptx::make_smem_desc(ap + ks * 2 * A_LBO, A_LBO, A_SBO);
-          uint64_t bd = ptx::make_smem_desc(bp + ks * 2 * B_SBO, /*LBO: k groups*/ B_SBO, /*SBO: n groups*/ B_LBO);
-          ptx::mma_f16_ss(dcol, ad, bd, idesc, (prod == 2) ? 1u : (ks > 0));
-        }
-      }
-      ptx::mma_commit(&ctl->bar_mma[tile]);
-    }
-  }
+  if (tid == 0) issue_gemm(true);
   // overlapped: adjoint of the AR(1) recurrence (warp 1) -> gradients of raw_e_bias, mu_e_bias, rho_e_bias
   if (m.full && w == 1) {
-    const float rho = ctl->rho, mu_e = ctl->mu_e, sig_rho = ctl->sig_rho, rterm = ctl->rho_term;
-    // reversed order: lane l handles t = T-1-8l-j
-    float A = 1.f, B = 0.f, u[8];
+    const float rho = ctl.rho, mu_e = ctl.mu_e, sig_rho = ctl.sig_rho, rterm = ctl.rho_term;
+    const float* ze = sQNZ() + m.nz_ze;
+    float* gze = sGNZ() + m.nz_ze;
+    float A = 1.f, B = 0.f, u[8];  // reversed order: lane l handles t = T-1-8l-j
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int t = T - 1 - (8 * l + j);
       float uj = 0.f, aj = 1.f;
-      if (t >= 0) { aj = rho; uj = sm.ebar[t]; }
+      if (t >= 0) { aj = rho; uj = sEBAR()[t]; }
       u[j] = uj; B = aj * B + uj; A = aj * A;
     }
     affine_scan(A, B, l);
@@ -536,159 +552,155 @@ __device__ __noinline__ void eval_point(const ModelDev& m, const Smem& sm, TC& t
       if (t >= 0) {
         ein = rho * ein + u[j];  // ebar[t]
         if (t >= 1) {
-          sm.gnz[m.nz_ze + t] = sig_rho * ein;
+          gze[t] = sig_rho * ein;
           s_mu += ein;
-          s_rho += ein * ((sm.e[t - 1] - mu_e) - sm.qnz[m.nz_ze + t] * rterm);
+          s_rho += ein * ((sE()[t - 1] - mu_e) - ze[t] * rterm);
         } else {
-          sm.gnz[m.nz_ze] = m.sig_e * ein;
+          gze[0] = m.sig_e * ein;
         }
       }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) { s_mu += __shfl_xor_sync(0xffffffffu, s_mu, off); s_rho += __shfl_xor_sync(0xffffffffu, s_rho, off); }
     if (l == 0) {
-      sm.gnz[m.nz_umu] = 0.02f * (1.0f - rho) * s_mu;
+      sGNZ()[m.nz_umu] = 0.02f * (1.0f - rho) * s_mu;
       const float d_rho = s_rho - (rho - 0.7f) * 100.0f;
       // stored as (d lp/d u_rho + u_rho) so that the generic "theta - gnz" form yields -d lp/d u_rho
-      sm.gnz[m.nz_urho] = rho * (1.0f - rho) * d_rho + (1.0f - 2.0f * rho) + sm.qnz[m.nz_urho];
+      sGNZ()[m.nz_urho] = rho * (1.0f - rho) * d_rho + (1.0f - 2.0f * rho) + sQNZ()[m.nz_urho];
     }
   }
-  tc.ph ^= 1;  // bar_mma phases of GEMM 1 consumed
   // ---------------- P9: epilogue 2: H -> scratch
-  tmem_epilogue(m, sm, tc, m.inv_scale_G * (1.0f / 256.0f), false);
-  tc.ph ^= 1;
+  tmem_epilogue(m.inv_scale_G * (1.0f / 256.0f), false, 1);
   __syncthreads();  // S7
-  // ---------------- P10/P11: forward cumulative sum of H over days -> gradient of the walk block
-  {
+  // ---------------- P10: forward cumulative sum of H over days; row 254 = L0^T g_pb = sum_t H[:,t]
+  if (zlane) {
     float run0 = 0.f, run1 = 0.f;
-    if (tc.zlane) {
+    const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const int t = 16 * w + d;
-        if (t < T) { run0 += sm.scr[t * SCR_PITCH + 2 * l]; run1 += sm.scr[t * SCR_PITCH + 2 * l + 1]; }
-        c[2 * d] = run0; c[2 * d + 1] = run1;
-      }
-      sm.tot[w * 52 + 2 * l] = run0;
-      sm.tot[w * 52 + 2 * l + 1] = run1;
+    for (int d = 0; d < 16; ++d) {
+      if (d < nd) { run0 += hz[d * SCR_PITCH]; run1 += hz[d * SCR_PITCH + 1]; }
+      c[2 * d] = run0; c[2 * d + 1] = run1;
     }
+    *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
+  }
+  if (tid < S) {  // gradient sources of raw_mu_b_T and raw_polling_bias share the spare GEMM row
+    const float h = sSCR()[PB_ROW * SCR_PITCH + tid];
+    sGNZ()[m.nz_zT + tid] = m.a_T * h;
+    sGNZ()[m.nz_zb + tid] = m.a_b * h;
   }
   __syncthreads();  // S8
+  // ---------------- P11: gradient of U in owner layout -> TMEM
   {
-    // every lane computes its 16-element half in (lane-divergent) arithmetic, then the whole warp
-    // converges for the .sync.aligned TMEM store
+    const uint32_t tp = tpriv();
     float carry0 = 0.f, carry1 = 0.f;
-    if (tc.zlane)
-      for (int w2 = 0; w2 < w; ++w2) { carry0 += sm.tot[w2 * 52 + 2 * l]; carry1 += sm.tot[w2 * 52 + 2 * l + 1]; }
+    if (zlane)
+      for (int w2 = 0; w2 < w; ++w2) {
+        const float2 t2 = *reinterpret_cast<const float2*>(sTOT() + w2 * 52 + 2 * l);
+        carry0 += t2.x; carry1 += t2.y;
+      }
+    const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
+    const float* gn = sGNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
+    const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float g[16];
-      if (tc.zlane) {
+      if (zlane) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int e = h * 16 + j, d = e >> 1, b = e & 1, t = 16 * w + d;
-          float v = 0.f;
-          if (t < T && 2 * l + b < S) {
-            const float z = sm.qz[t * QZ_PITCH + 2 * l + b];
-            v = (t <= T - 2) ? z - m.a_w * (c[e] + (b ? carry1 : carry0)) : z;
-          }
-          g[j] = v;
+        for (int j = 0; j < 16; j += 2) {
+          const int d = (h * 16 + j) >> 1;
+          const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
+          const bool walk = d < ndw;
+          g[j] = walk ? fmaf(-m.a_w, c[2 * d] + carry0, z.x) : z.x;
+          g[j + 1] = walk ? fmaf(-m.a_w, c[2 * d + 1] + carry1, z.y) : z.y;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = tc.nz0 + h * 16 + j;
-          float v = 0.f;
-          if (k < m.NZ) {
-            const float th = sm.qnz[k];
-            float gs;
-            if (k >= m.nz_zT && k < m.nz_zT + S) {
-              float s = 0.f;
-              for (int w2 = 0; w2 < NWARP; ++w2) s += sm.tot[w2 * 52 + (k - m.nz_zT)];
-              gs = m.a_T * s;
-            } else if (k >= m.nz_zb && k < m.nz_zb + S) {
-              gs = m.a_b * sm.scr[PB_ROW * SCR_PITCH + (k - m.nz_zb)];
-            } else {
-              gs = sm.gnz[k];
-            }
-            v = th - gs;
-          }
-          g[j] = v;
+        for (int j = 0; j < 16; j += 4) {
+          const float4 th = *reinterpret_cast<const float4*>(qn + h * 16 + j);
+          const float4 gs = *reinterpret_cast<const float4*>(gn + h * 16 + j);
+          g[j] = th.x - gs.x; g[j + 1] = th.y - gs.y; g[j + 2] = th.z - gs.z; g[j + 3] = th.w - gs.w;
         }
       }
       __syncwarp();
-      tm_st16(tc, TM_G + 16 * h, g);
+      tm_st16(tp, TM_G + 16 * h, g);
     }
     ptx::tmem_wait_st();
   }
-  // note: callers synchronise before reading ctl->U
+  // note: callers synchronise before reading ctl.U
 }
 
 // ================================================================================================
 // small block-wide helpers
 // ================================================================================================
-// sum of squares reduction -> every thread gets the total (fixed summation order)
-__device__ __forceinline__ float block_sum_f(const Smem& sm, const TC& tc, float v) {
+// block sum, every thread gets the total (fixed summation order); `buf` alternates between uses that
+// are not separated by another barrier
+__device__ __forceinline__ float block_sum_f(float v, int buf) {
+  const int tid = threadIdx.x;
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-  __syncthreads();  // protect kred against the previous use
-  if (tc.l == 0) sm.ctl->kred[tc.w] = v;
+  float* kred = CTL().kred[buf];
+  if ((tid & 31) == 0) kred[tid >> 5] = v;
   __syncthreads();
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < NWARP; ++i) s += sm.ctl->kred[i];
-  return s;
+  const float4 a = *reinterpret_cast<const float4*>(kred), b = *reinterpret_cast<const float4*>(kred + 4);
+  const float4 c = *reinterpret_cast<const float4*>(kred + 8), d = *reinterpret_cast<const float4*>(kred + 12);
+  return (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
 }
 
 // momentum refresh: P ~ N(0, I) in whitened coordinates -> TMEM column block `col`; returns |P|^2 partial
-__device__ __forceinline__ float draw_momentum(const RunArgs& a, const TC& tc, uint32_t chain_gid, uint32_t iter, uint32_t stream,
+__device__ __forceinline__ float draw_momentum(const RunArgs& a, uint32_t tp, uint32_t chain_gid, uint32_t iter, uint32_t stream,
                                                uint32_t sub, uint32_t col) {
   float ss = 0.f;
+  const int32_t* map = a.m.map_i2s + threadIdx.x;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int si = a.m.map_i2s[(h * 16 + j) * NT + tc.tid];
+      const int si = map[(h * 16 + j) * NT];
       v[j] = (si >= 0) ? rng_normal(a.seed, chain_gid, (uint32_t)si, iter, stream, sub) : 0.f;
       ss += v[j] * v[j];
     }
-    tm_st16(tc, col + 16 * h, v);
+    tm_st16(tp, col + 16 * h, v);
   }
   ptx::tmem_wait_st();
   return ss;
 }
 
-// Phase A of a leaf: P = p_half - h*s*g (full-step momentum) -> TM_TMP; returns |P|^2 partial.
-__device__ __forceinline__ float full_step_momentum(const TC& tc, float hs) {
+// Phase A of a leaf: P = p_half - hs*s*g (full-step momentum) -> TM_TMP; returns |P|^2 partial.
+__device__ __forceinline__ float full_step_momentum(uint32_t tp, float hs) {
   float ss = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float p[16], s[16], g[16];
-    tm_ld16(tc, TM_P + 16 * h, p);
-    tm_ld16(tc, TM_S + 16 * h, s);
-    tm_ld16(tc, TM_G + 16 * h, g);
+    tm_ld16(tp, TM_P + 16 * h, p);
+    tm_ld16(tp, TM_S + 16 * h, s);
+    tm_ld16(tp, TM_G + 16 * h, g);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { p[j] = p[j] - hs * s[j] * g[j]; ss += p[j] * p[j]; }
-    tm_st16(tc, TM_TMP + 16 * h, p);
+    for (int j = 0; j < 16; ++j) { p[j] = fmaf(-hs * s[j], g[j], p[j]); ss = fmaf(p[j], p[j], ss); }
+    tm_st16(tp, TM_TMP + 16 * h, p);
   }
   ptx::tmem_wait_st();
   return ss;
 }
 // Phase C: p_half' = 2P - p_half ; q' = q + eps_signed * s * p_half'
-__device__ __forceinline__ void advance(const ModelDev& m, const Smem& sm, const TC& tc, float eps_signed) {
+__device__ __forceinline__ void advance(uint32_t tp, float eps_signed) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float p[16], s[16], P[16];
-    tm_ld16(tc, TM_P + 16 * h, p);
-    tm_ld16(tc, TM_S + 16 * h, s);
-    tm_ld16(tc, TM_TMP + 16 * h, P);
+    tm_ld16(tp, TM_P + 16 * h, p);
+    tm_ld16(tp, TM_S + 16 * h, s);
+    tm_ld16(tp, TM_TMP + 16 * h, P);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 16; j += 2) {
       p[j] = 2.0f * P[j] - p[j];
-      const int e = h * 16 + j;
-      if (elem_valid(m, tc, e)) { float* q = q_elem(sm, tc, e); *q = *q + eps_signed * s[j] * p[j]; }
+      p[j + 1] = 2.0f * P[j + 1] - p[j + 1];
+      float2* q = qpair((h * 16 + j) >> 1);
+      float2 v = *q;
+      v.x = fmaf(eps_signed * s[j], p[j], v.x);
+      v.y = fmaf(eps_signed * s[j + 1], p[j + 1], v.y);
+      *q = v;
     }
-    tm_st16(tc, TM_P + 16 * h, p);
+    tm_st16(tp, TM_P + 16 * h, p);
   }
   ptx::tmem_wait_st();
 }
@@ -696,35 +708,53 @@ __device__ __forceinline__ void advance(const ModelDev& m, const Smem& sm, const
 // One U-turn merge (Stan's three criteria) between the completed left subtree L = {b,e,r} and the
 // implicit right subtree R = {b: rb (or P if null), r: P + S, e: P}; S (TM_G) += L.r afterwards.
 // `first` : S is implicitly zero.   `single`: L.b = L.e = L.r (Left_0).
-__device__ __forceinline__ bool merge_check(const Smem& sm, const TC& tc, const float* Lb, const float* Le, const float* Lr,
-                                            const float* Rb, bool first, bool single) {
+__device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first,
+                                            bool single) {
+  const int tid = threadIdx.x;
   float c1a = 0.f, c1b = 0.f, c2a = 0.f, c2b = 0.f, c3a = 0.f, c3b = 0.f;
+  if (single) {
+    // Left_0 = one leaf `a`, right = this leaf: rho = a + P and the three criteria reduce to a.(a+P) > 0, P.(a+P) > 0
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float P[16], S[16];
+      tm_ld16(tp, TM_TMP + 16 * h, P);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float lr = Lr[(h * 16 + j) * NT + tid];
+        const float x = lr + P[j];
+        c1a = fmaf(lr, x, c1a); c1b = fmaf(P[j], x, c1b);
+        S[j] = lr;
+      }
+      tm_st16(tp, TM_G + 16 * h, S);
+    }
+    c2a = c3a = 1.f; c2b = c3b = 1.f;
+  } else
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float P[16], S[16];
-    tm_ld16(tc, TM_TMP + 16 * h, P);
+    tm_ld16(tp, TM_TMP + 16 * h, P);
     if (first) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) S[j] = 0.f;
     } else {
-      tm_ld16(tc, TM_G + 16 * h, S);
+      tm_ld16(tp, TM_G + 16 * h, S);
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int gi = (h * 16 + j) * NT + tc.tid;
+      const int gi = (h * 16 + j) * NT + tid;
       const float lr = Lr[gi];
-      const float lb = single ? lr : Lb[gi];
-      const float le = single ? lr : Le[gi];
+      const float lb = Lb[gi];
+      const float le = Le[gi];
       const float rb = (Rb == nullptr) ? P[j] : Rb[gi];
       const float x = lr + S[j] + P[j];
-      c1a += lb * x; c1b += P[j] * x;
+      c1a = fmaf(lb, x, c1a); c1b = fmaf(P[j], x, c1b);
       const float y = lr + rb;
-      c2a += lb * y; c2b += rb * y;
+      c2a = fmaf(lb, y, c2a); c2b = fmaf(rb, y, c2b);
       const float z = S[j] + P[j] + le;
-      c3a += le * z; c3b += P[j] * z;
+      c3a = fmaf(le, z, c3a); c3b = fmaf(P[j], z, c3b);
       S[j] += lr;
     }
-    tm_st16(tc, TM_G + 16 * h, S);
+    tm_st16(tp, TM_G + 16 * h, S);
   }
   ptx::tmem_wait_st();
   float v[6] = {c1a, c1b, c2a, c2b, c3a, c3b};
@@ -733,25 +763,27 @@ __device__ __forceinline__ bool merge_check(const Smem& sm, const TC& tc, const 
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
   }
-  __syncthreads();
-  if (tc.l == 0) {
+  Ctl& ctl = CTL();
+  if ((tid & 31) == 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) sm.ctl->mred[tc.w][i] = v[i];
+    for (int i = 0; i < 6; ++i) ctl.mred[tid >> 5][i] = v[i];
   }
   __syncthreads();
   bool pred = true;
-  if (tc.tid < 6) {
+  if (tid < 6) {
     float s = 0.f;
-    for (int w2 = 0; w2 < NWARP; ++w2) s += sm.ctl->mred[w2][tc.tid];
+#pragma unroll
+    for (int w2 = 0; w2 < NWARP; ++w2) s += ctl.mred[w2][tid];
     pred = s > 0.f;
   }
   return __syncthreads_and(pred) != 0;
 }
 
-__device__ __forceinline__ double logaddexp_d(double a, double b) {
-  if (a == -CUDART_INF) return b;
-  if (b == -CUDART_INF) return a;
-  return a > b ? a + log1p(exp(b - a)) : b + log1p(exp(a - b));
+__device__ __forceinline__ float logaddexp_f(float a, float b) {
+  if (a == -CUDART_INF_F) return b;
+  if (b == -CUDART_INF_F) return a;
+  const float mx = fmaxf(a, b), mn = fminf(a, b);
+  return mx + log1pf(__expf(mn - mx));
 }
 
 struct TransStats { float lp, accept, eps, depth, nleap, divergent, energy; };
@@ -761,48 +793,52 @@ struct TransStats { float lp, accept, eps, depth, nleap, divergent, energy; };
 // TM_S = sqrt(inverse metric).  On exit q(smem) = new sample.  `em`: outputs for the ENTRY point
 // (the previous iteration's draw), emitted during the initial gradient evaluation.
 // ================================================================================================
-__device__ __noinline__ void transition(const RunArgs& a, const Smem& sm, TC& tc, float* ws, uint32_t chain_gid, uint32_t iter,
-                                        float eps, const Emit em, TransStats& st) {
-  const ModelDev& m = a.m;
-  Ctl* ctl = sm.ctl;
+__device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t chain_gid, uint32_t iter, float eps, const Emit em,
+                                        TransStats& st) {
+  Ctl& ctl = CTL();
+  const uint32_t tp = tpriv();
+  const int tid = threadIdx.x;
   // fresh whitened momentum into TM_P, gradient at the current point
-  float ksq = draw_momentum(a, tc, chain_gid, iter, 1, 0, TM_P);
-  eval_point(m, sm, tc, em);
-  ksq = block_sum_f(sm, tc, ksq);  // (contains the barrier that publishes ctl->U)
-  const double U0 = ctl->U;
+  float ksq = draw_momentum(a, tp, chain_gid, iter, 1, 0, TM_P);
+  eval_point(em);
+  ksq = block_sum_f(ksq, 0);  // (its barrier also publishes ctl.U)
+  const double U0 = ctl.U;
   const double H0 = U0 + 0.5 * (double)ksq;
   // the two trajectory ends, stored mid-leapfrog: (q +- eps s p_half, p_half), and the tree summary
   {
     const float hs = 0.5f * eps;
+    float* g = ws + tid;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float P[16], s[16], g[16];
-      tm_ld16(tc, TM_P + 16 * h, P);
-      tm_ld16(tc, TM_S + 16 * h, s);
-      tm_ld16(tc, TM_G + 16 * h, g);
+      float P[16], s[16], gr[16];
+      tm_ld16(tp, TM_P + 16 * h, P);
+      tm_ld16(tp, TM_S + 16 * h, s);
+      tm_ld16(tp, TM_G + 16 * h, gr);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int e = h * 16 + j, gi = e * NT + tc.tid;
-        const bool ok = elem_valid(m, tc, e);
-        const float q0 = ok ? *q_elem(sm, tc, e) : 0.f;
-        const float pf = P[j] - hs * s[j] * g[j], pb = P[j] + hs * s[j] * g[j];
-        slot_ptr(ws, SLOT_ENDF_P)[gi] = pf;
-        slot_ptr(ws, SLOT_ENDB_P)[gi] = pb;
-        slot_ptr(ws, SLOT_ENDF_Q)[gi] = q0 + eps * s[j] * pf;
-        slot_ptr(ws, SLOT_ENDB_Q)[gi] = q0 - eps * s[j] * pb;
-        slot_ptr(ws, SLOT_TOP_BB)[gi] = P[j];
-        slot_ptr(ws, SLOT_TOP_FF)[gi] = P[j];
-        slot_ptr(ws, SLOT_TOP_RHO)[gi] = P[j];
-        slot_ptr(ws, SLOT_CAND_A)[gi] = q0;
+      for (int j = 0; j < 16; j += 2) {
+        const float2 q0 = *qpair((h * 16 + j) >> 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const size_t gi = (size_t)(h * 16 + j + b) * NT;
+          const float qq = b ? q0.y : q0.x;
+          const float pf = fmaf(-hs * s[j + b], gr[j + b], P[j + b]), pb = fmaf(hs * s[j + b], gr[j + b], P[j + b]);
+          g[(size_t)SLOT_ENDF_P * VEC + gi] = pf;
+          g[(size_t)SLOT_ENDB_P * VEC + gi] = pb;
+          g[(size_t)SLOT_ENDF_Q * VEC + gi] = fmaf(eps * s[j + b], pf, qq);
+          g[(size_t)SLOT_ENDB_Q * VEC + gi] = fmaf(-eps * s[j + b], pb, qq);
+          g[(size_t)SLOT_TOP_BB * VEC + gi] = P[j + b];
+          g[(size_t)SLOT_TOP_FF * VEC + gi] = P[j + b];
+          g[(size_t)SLOT_TOP_RHO * VEC + gi] = P[j + b];
+          g[(size_t)SLOT_CAND_A * VEC + gi] = qq;
+        }
       }
     }
   }
   int samp = SLOT_CAND_A, prop = SLOT_CAND_B;
   double U_samp = U0, H_samp = H0, U_prop = U0, H_prop = H0;
-  double lsw = 0.0, sum_metro = 0.0;
+  float lsw = 0.f, sum_metro = 0.f;
   int n_leap = 0, depth = 0, loaded = 0;
   bool divergent = false;
-  __syncthreads();  // global slot writes by this block are ordered for later reads by the same threads anyway
 
   while (depth < a.max_depth) {
     uint32_t rw[4];
@@ -810,71 +846,73 @@ __device__ __noinline__ void transition(const RunArgs& a, const Smem& sm, TC& tc
     const int dir = (rw[0] >> 31) ? 1 : -1;  // u > 0.5
     if (loaded != dir) {
       if (loaded != 0) {
-        q_to_global(m, sm, tc, slot_ptr(ws, loaded > 0 ? SLOT_ENDF_Q : SLOT_ENDB_Q));
-        tm_to_global(tc, TM_P, slot_ptr(ws, loaded > 0 ? SLOT_ENDF_P : SLOT_ENDB_P));
+        q_to_global(slot_ptr(ws, loaded > 0 ? SLOT_ENDF_Q : SLOT_ENDB_Q));
+        tm_to_global(tp, TM_P, slot_ptr(ws, loaded > 0 ? SLOT_ENDF_P : SLOT_ENDB_P));
       }
-      __syncthreads();
-      global_to_q(m, sm, tc, slot_ptr(ws, dir > 0 ? SLOT_ENDF_Q : SLOT_ENDB_Q));
-      global_to_tm(tc, TM_P, slot_ptr(ws, dir > 0 ? SLOT_ENDF_P : SLOT_ENDB_P));
+      global_to_q(slot_ptr(ws, dir > 0 ? SLOT_ENDF_Q : SLOT_ENDB_Q));   // owner-only access: no barrier needed before
+      global_to_tm(tp, TM_P, slot_ptr(ws, dir > 0 ? SLOT_ENDF_P : SLOT_ENDB_P));
       loaded = dir;
+      ptx::tc_fence_before();
       __syncthreads();
     }
     const float eps_s = dir > 0 ? eps : -eps;
     const float hs = 0.5f * eps_s;
-    double lsw_sub = -CUDART_INF;
+    float lsw_sub = -CUDART_INF_F;
     bool ok = true, persist = true;
     const int nleaf = 1 << depth;
     for (int n = 0; n < nleaf; ++n) {
-      Emit none{nullptr, nullptr, nullptr};
-      eval_point(m, sm, tc, none);
-      float kk = full_step_momentum(tc, hs);
-      kk = block_sum_f(sm, tc, kk);
-      double h = ctl->U + 0.5 * (double)kk;
+      const Emit none{nullptr, nullptr, nullptr};
+      eval_point(none);
+      float kk = full_step_momentum(tp, hs);
+      kk = block_sum_f(kk, n & 1);
+      double h = ctl.U + 0.5 * (double)kk;
       if (!(h == h)) h = CUDART_INF;
       ++n_leap;
+      const float dH = (float)(H0 - h);  // energy differences are O(1): fp32 is ample for the weights
       if (h - H0 > 1000.0) divergent = true;
-      lsw_sub = logaddexp_d(lsw_sub, H0 - h);
-      sum_metro += (H0 - h > 0) ? 1.0 : exp(H0 - h);
+      lsw_sub = logaddexp_f(lsw_sub, dH);
+      sum_metro += (dH > 0.f) ? 1.0f : __expf(dH);
       if (divergent) { ok = false; break; }
       // multinomial selection inside the new subtree (reservoir form of Stan's pairwise rule)
       {
         uint32_t sw[4];
         rng_words(a.seed, chain_gid, (uint32_t)n_leap, iter, 3, 0, sw);
-        if (n == 0 || (double)u01(sw[0]) < exp((H0 - h) - lsw_sub)) {
-          q_to_global(m, sm, tc, slot_ptr(ws, prop));
-          U_prop = ctl->U; H_prop = h;
+        if (n == 0 || u01(sw[0]) < __expf(dH - lsw_sub)) {
+          q_to_global(slot_ptr(ws, prop));
+          U_prop = ctl.U; H_prop = h;
         }
       }
       // U-turn checks for every subtree this leaf completes
-      int t = 0;
-      while ((n >> t) & 1) ++t;
+      const int t = __ffs(~n) - 1;  // trailing ones of n
       for (int k = 0; k < t && ok; ++k) {
         if (k == 0) {
           const float* L0p = slot_ptr(ws, SLOT_LEFT0);
-          ok = merge_check(sm, tc, L0p, L0p, L0p, nullptr, true, true);
+          ok = merge_check(tp, L0p, L0p, L0p, nullptr, true, true);
         } else {
           const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
           const float* Rb = (k == 1) ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (k - 2));
-          ok = merge_check(sm, tc, Lk, Lk + VEC, Lk + 2 * VEC, Rb, false, false);
+          ok = merge_check(tp, Lk, Lk + VEC, Lk + 2 * VEC, Rb, false, false);
         }
       }
       if (!ok) break;
       if (n < nleaf - 1) {
         // this subtree becomes the stored left half at level t: {b, e, r}
         if (t == 0) {
-          tm_to_global(tc, TM_TMP, slot_ptr(ws, SLOT_LEFT0));
+          tm_to_global(tp, TM_TMP, slot_ptr(ws, SLOT_LEFT0));
         } else {
-          float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1));
-          const float* Bsrc = (t == 1) ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (t - 2));
+          float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1)) + tid;
+          const float* Bsrc = ((t == 1) ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (t - 2))) + tid;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            float P[16], S[16];
-            tm_ld16(tc, TM_TMP + 16 * hh, P);
-            tm_ld16(tc, TM_G + 16 * hh, S);
+            float P[16], S[16], B[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) B[j] = Bsrc[(hh * 16 + j) * NT];
+            tm_ld16(tp, TM_TMP + 16 * hh, P);
+            tm_ld16(tp, TM_G + 16 * hh, S);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int gi = (hh * 16 + j) * NT + tc.tid;
-              Lt[gi] = Bsrc[gi];
+              const int gi = (hh * 16 + j) * NT;
+              Lt[gi] = B[j];
               Lt[VEC + gi] = P[j];
               Lt[2 * VEC + gi] = P[j] + S[j];
             }
@@ -886,85 +924,87 @@ __device__ __noinline__ void transition(const RunArgs& a, const Smem& sm, TC& tc
         const float* F = slot_ptr(ws, dir > 0 ? SLOT_TOP_BB : SLOT_TOP_FF);
         const float* A = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB);
         const float* Rb = (depth == 0) ? nullptr : (depth == 1 ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (depth - 2)));
-        persist = merge_check(sm, tc, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0, false);
-        float* rho = slot_ptr(ws, SLOT_TOP_RHO);
-        float* endv = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB);
+        persist = merge_check(tp, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0, false);
+        float* rho = slot_ptr(ws, SLOT_TOP_RHO) + tid;
+        float* endv = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB) + tid;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float P[16], S[16];
-          tm_ld16(tc, TM_TMP + 16 * hh, P);
-          tm_ld16(tc, TM_G + 16 * hh, S);  // = old rho_top + sum of lower lefts
+          tm_ld16(tp, TM_TMP + 16 * hh, P);
+          tm_ld16(tp, TM_G + 16 * hh, S);  // = old rho_top + sum of lower lefts
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int gi = (hh * 16 + j) * NT + tc.tid;
+            const int gi = (hh * 16 + j) * NT;
             rho[gi] = S[j] + P[j];
             endv[gi] = P[j];
           }
         }
       }
-      advance(m, sm, tc, eps_s);
+      advance(tp, eps_s);
       ptx::tc_fence_before();
       __syncthreads();
     }
     if (!ok) break;
     ++depth;
     // biased progressive sampling at the top level
-    if (lsw_sub > lsw || (double)u01(rw[1]) < exp(lsw_sub - lsw)) {
+    if (lsw_sub > lsw || u01(rw[1]) < __expf(lsw_sub - lsw)) {
       const int tmp = samp; samp = prop; prop = tmp;
       U_samp = U_prop; H_samp = H_prop;
     }
-    lsw = logaddexp_d(lsw, lsw_sub);
+    lsw = logaddexp_f(lsw, lsw_sub);
     if (!persist) break;
   }
-  __syncthreads();
-  global_to_q(m, sm, tc, slot_ptr(ws, samp));
+  global_to_q(slot_ptr(ws, samp));
   ptx::tc_fence_before();
   __syncthreads();
   st.lp = (float)(-U_samp);  // centred; the host adds lp_const in fp64 (fp32 cannot hold -1.2e6 to 1e-2)
-  st.accept = (float)(sum_metro / (double)(n_leap > 0 ? n_leap : 1));
+  st.accept = sum_metro / (float)(n_leap > 0 ? n_leap : 1);
   st.eps = eps; st.depth = (float)depth; st.nleap = (float)n_leap; st.divergent = divergent ? 1.f : 0.f;
   st.energy = (float)H_samp;
-  if (tc.tid == 0) { ctl->cs.n_leapfrog += n_leap; ctl->cs.U = (float)U_samp; }
+  if (tid == 0) { ctl.cs.n_leapfrog += n_leap; ctl.cs.U = (float)U_samp; }
 }
 
 // Stan base_hmc::init_stepsize: double / halve eps until the one-step acceptance crosses 0.8
-__device__ __noinline__ float find_stepsize(const RunArgs& a, const Smem& sm, TC& tc, float* ws, uint32_t chain_gid, uint32_t iter_tag,
-                                            float eps) {
-  const ModelDev& m = a.m;
-  Ctl* ctl = sm.ctl;
+__device__ __noinline__ float find_stepsize(const RunArgs& a, float* ws, uint32_t chain_gid, uint32_t iter_tag, float eps) {
+  Ctl& ctl = CTL();
+  const uint32_t tp = tpriv();
   if (!(eps > 0.f) || eps > 1e7f) return eps;
-  q_to_global(m, sm, tc, slot_ptr(ws, SLOT_TMPQ));
+  q_to_global(slot_ptr(ws, SLOT_TMPQ));
   int direction = 0;
   const Emit none{nullptr, nullptr, nullptr};
   for (uint32_t attempt = 0; attempt < 200; ++attempt) {
     __syncthreads();
-    global_to_q(m, sm, tc, slot_ptr(ws, SLOT_TMPQ));
+    global_to_q(slot_ptr(ws, SLOT_TMPQ));
+    float k0 = draw_momentum(a, tp, chain_gid, iter_tag, 5, attempt, TM_P);
+    ptx::tc_fence_before();
     __syncthreads();
-    float k0 = draw_momentum(a, tc, chain_gid, iter_tag, 5, attempt, TM_P);
-    eval_point(m, sm, tc, none);
-    k0 = block_sum_f(sm, tc, k0);
-    const double H0 = ctl->U + 0.5 * (double)k0;
+    eval_point(none);
+    k0 = block_sum_f(k0, 0);
+    const double H0 = ctl.U + 0.5 * (double)k0;
     // first half step + position step
-    full_step_momentum(tc, 0.5f * eps);  // TM_TMP = p - eps/2 s g  (= p_half)
+    full_step_momentum(tp, 0.5f * eps);  // TM_TMP = p - eps/2 s g  (= p_half)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float p[16], s[16];
-      tm_ld16(tc, TM_TMP + 16 * h, p);
-      tm_ld16(tc, TM_S + 16 * h, s);
+      tm_ld16(tp, TM_TMP + 16 * h, p);
+      tm_ld16(tp, TM_S + 16 * h, s);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int e = h * 16 + j;
-        if (elem_valid(m, tc, e)) { float* q = q_elem(sm, tc, e); *q = *q + eps * s[j] * p[j]; }
+      for (int j = 0; j < 16; j += 2) {
+        float2* q = qpair((h * 16 + j) >> 1);
+        float2 v = *q;
+        v.x = fmaf(eps * s[j], p[j], v.x);
+        v.y = fmaf(eps * s[j + 1], p[j + 1], v.y);
+        *q = v;
       }
-      tm_st16(tc, TM_P + 16 * h, p);
+      tm_st16(tp, TM_P + 16 * h, p);
     }
     ptx::tmem_wait_st();
     ptx::tc_fence_before();
     __syncthreads();
-    eval_point(m, sm, tc, none);
-    float k1 = full_step_momentum(tc, 0.5f * eps);
-    k1 = block_sum_f(sm, tc, k1);
-    double h = ctl->U + 0.5 * (double)k1;
+    eval_point(none);
+    float k1 = full_step_momentum(tp, 0.5f * eps);
+    k1 = block_sum_f(k1, 1);
+    double h = ctl.U + 0.5 * (double)k1;
     if (!(h == h)) h = CUDART_INF;
     const double dH = H0 - h;
     const double thr = log(0.8);
@@ -975,7 +1015,7 @@ __device__ __noinline__ float find_stepsize(const RunArgs& a, const Smem& sm, TC
     if (eps > 1e7f || eps == 0.f) break;
   }
   __syncthreads();
-  global_to_q(m, sm, tc, slot_ptr(ws, SLOT_TMPQ));
+  global_to_q(slot_ptr(ws, SLOT_TMPQ));
   ptx::tc_fence_before();
   __syncthreads();
   return eps;
@@ -984,163 +1024,158 @@ __device__ __noinline__ float find_stepsize(const RunArgs& a, const Smem& sm, TC
 // ================================================================================================
 // kernels
 // ================================================================================================
-__device__ __forceinline__ void cta_setup(const ModelDev& m, const Smem& sm, TC& tc, unsigned char* base) {
-  tc.tid = threadIdx.x; tc.w = tc.tid >> 5; tc.l = tc.tid & 31;
-  tc.zlane = tc.l < ZLANES; tc.nzlane = !tc.zlane;
-  tc.nz0 = (tc.w * NZ_LANES + (tc.l - ZLANES)) * EPT;
-  tc.ph = 0;
-  Ctl* ctl = sm.ctl;
-  if (tc.w == 0) { ptx::tmem_alloc(&ctl->tmem_base, 512); ptx::tmem_relinquish(); }
-  if (tc.tid == 0) {
-    ptx::mbar_init(&ctl->bar_mma[0], 1);
-    ptx::mbar_init(&ctl->bar_mma[1], 1);
-    ptx::mbar_init(&ctl->bar_load, 1);
+__device__ __forceinline__ void cta_setup(const ModelDev& mg) {
+  const int tid = threadIdx.x, w = tid >> 5;
+  Ctl& ctl = CTL();
+  if (w == 0) { ptx::tmem_alloc(&ctl.tmem_base, 512); ptx::tmem_relinquish(); }
+  if (tid == 0) {
+    ptx::mbar_init(&ctl.bar_mma[0], 1);
+    ptx::mbar_init(&ctl.bar_mma[1], 1);
+    ptx::mbar_init(&ctl.bar_load, 1);
     ptx::fence_mbar_init();
   }
-  // zero all of shared memory that holds padded vectors
-  for (int i = tc.tid; i < (int)((SM_CTL - SM_QZ) / 4); i += NT) reinterpret_cast<float*>(base + SM_QZ)[i] = 0.f;
+  // zero every padded vector in shared memory; copy the model block
+  for (int i = tid; i < (int)((SM_CTL - SM_QZ) / 4); i += NT) SMP(float, SM_QZ)[i] = 0.f;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&mg);
+    for (int i = tid; i < (int)(sizeof(ModelDev) / 4); i += NT) SMP(uint32_t, SM_MODEL)[i] = src[i];
+  }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   // constants: TMA bulk copies (global -> shared), one mbarrier
-  if (tc.tid == 0) {
+  if (tid == 0) {
     const uint32_t bytes = 2 * B_PLANE + 5 * NPOLL_CAP * 4 + 64 * 4;
-    ptx::mbar_expect_tx(&ctl->bar_load, bytes);
-    ptx::bulk_g2s(sm.b, m.btiles, 2 * B_PLANE, &ctl->bar_load);
-    ptx::bulk_g2s(sm.pk_idx, m.pk, 5 * NPOLL_CAP * 4, &ctl->bar_load);
-    ptx::bulk_g2s(sm.prior, m.prior, 64 * 4, &ctl->bar_load);
+    ptx::mbar_expect_tx(&ctl.bar_load, bytes);
+    ptx::bulk_g2s(smem_raw + SM_B, mg.btiles, 2 * B_PLANE, &ctl.bar_load);
+    ptx::bulk_g2s(smem_raw + SM_PK, mg.pk, 5 * NPOLL_CAP * 4, &ctl.bar_load);
+    ptx::bulk_g2s(smem_raw + SM_PRIOR, mg.prior, 64 * 4, &ctl.bar_load);
   }
-  ptx::mbar_wait(&ctl->bar_load, 0);
-  tc.tpriv = ctl->tmem_base + ((uint32_t)((tc.w & 3) * 32) << 16) + (uint32_t)(tc.w >> 2) * 32;
-  __syncthreads();
-}
-__device__ __forceinline__ void cta_teardown(const Smem& sm, const TC& tc) {
+  ptx::mbar_wait(&ctl.bar_load, 0);
+  // zero the resident TMEM vectors (padding slots must hold zeros)
+  {
+    float z[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) z[j] = 0.f;
+    const uint32_t tp = tpriv();
+    tm_st16(tp, TM_P, z); tm_st16(tp, TM_P + 16, z); tm_st16(tp, TM_S, z); tm_st16(tp, TM_S + 16, z);
+    ptx::tmem_wait_st();
+  }
   ptx::tc_fence_before();
   __syncthreads();
-  if (tc.w == 0) ptx::tmem_dealloc(sm.ctl->tmem_base, 512);
+}
+__device__ __forceinline__ void cta_teardown() {
+  ptx::tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) ptx::tmem_dealloc(CTL().tmem_base, 512);
 }
 
 // test hook: log density + gradient for n positions (potus_logp_grad)
 extern "C" __global__ void __launch_bounds__(NT, 1) potus_eval_kernel(const __grid_constant__ EvalArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  Smem sm = carve(base);
-  TC tc;
-  cta_setup(a.m, sm, tc, base);
+  cta_setup(a.m);
+  const uint32_t tp = tpriv();
   for (int i = blockIdx.x; i < a.n; i += gridDim.x) {
-    global_to_q(a.m, sm, tc, a.q_in + (size_t)i * VEC);
+    global_to_q(a.q_in + (size_t)i * VEC);
     __syncthreads();
-    Emit em{nullptr, nullptr, a.mu_out ? a.mu_out + (size_t)i * a.m.S * a.m.T : nullptr};
-    eval_point(a.m, sm, tc, em);
+    const Emit em{nullptr, nullptr, a.mu_out ? a.mu_out + (size_t)i * a.m.S * a.m.T : nullptr};
+    eval_point(em);
     __syncthreads();
-    tm_to_global(tc, TM_G, a.g_out + (size_t)i * VEC);
-    if (tc.tid == 0) a.u_out[i] = sm.ctl->U;
+    tm_to_global(tp, TM_G, a.g_out + (size_t)i * VEC);
+    if (threadIdx.x == 0) a.u_out[i] = CTL().U;
     ptx::tc_fence_before();
     __syncthreads();
   }
-  cta_teardown(sm, tc);
-}
-
-// Welford update of the per-chain posterior variance estimate (Stan var_adaptation), owner layout
-__device__ __forceinline__ void welford_add(const ModelDev& m, const Smem& sm, const TC& tc, float* mean, float* m2, int nsamp) {
-  const float inv = 1.0f / (float)nsamp;
-#pragma unroll 8
-  for (int e = 0; e < EPT; ++e) {
-    if (!elem_valid(m, tc, e)) continue;
-    const int gi = e * NT + tc.tid;
-    const float q = *q_elem(sm, tc, e);
-    const float mu = mean[gi], d = q - mu, mu2 = mu + d * inv;
-    mean[gi] = mu2;
-    m2[gi] += (q - mu2) * d;
-  }
+  cta_teardown();
 }
 
 extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __grid_constant__ RunArgs a) {
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-  Smem sm = carve(base);
-  TC tc;
-  const ModelDev& m = a.m;
-  cta_setup(m, sm, tc, base);
-  Ctl* ctl = sm.ctl;
+  cta_setup(a.m);
+  const ModelDev& m = MD();
+  Ctl& ctl = CTL();
+  const int tid = threadIdx.x;
+  const uint32_t tp = tpriv();
   float* ws = a.workspace + (size_t)blockIdx.x * NSLOT * VEC;
   const int n_iter_total = a.iter_warmup + a.iter_sampling;
   const Emit none{nullptr, nullptr, nullptr};
 
   for (;;) {
     __syncthreads();
-    if (tc.tid == 0) ctl->chain = atomicAdd(a.queue, 1);
+    if (tid == 0) ctl.chain = atomicAdd(a.queue, 1);
     __syncthreads();
-    const int chain = ctl->chain;
+    const int chain = ctl.chain;
     if (chain >= a.n_chains) break;
     const uint32_t gid = (uint32_t)(a.chain_id_offset + chain);
     float* qg = a.q + (size_t)chain * VEC;
     float* sg = a.sqrt_m + (size_t)chain * VEC;
-    float* wmean = a.wf_mean + (size_t)chain * VEC;
-    float* wm2 = a.wf_m2 + (size_t)chain * VEC;
-    if (tc.tid == 0) ctl->cs = a.cs[chain];
+    float* wmean = a.wf_mean + (size_t)chain * VEC + tid;
+    float* wm2 = a.wf_m2 + (size_t)chain * VEC + tid;
+    const int32_t* map = a.m.map_i2s + tid;
+    if (tid == 0) ctl.cs = a.cs[chain];
     __syncthreads();
 
     if (a.do_init) {
+      // unit metric (zero in padding slots so that padding never moves)
+      {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float one[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) one[j] = (map[(h * 16 + j) * NT] >= 0) ? 1.0f : 0.f;
+          tm_st16(tp, TM_S + 16 * h, one);
+        }
+        ptx::tmem_wait_st();
+      }
       // ---- random inits U(-r, r) on the unconstrained scale; retry while U / gradient are not finite
       bool good = false;
       for (uint32_t attempt = 0; attempt < 100 && !good; ++attempt) {
-#pragma unroll 4
-        for (int e = 0; e < EPT; ++e) {
-          const int si = m.map_i2s[e * NT + tc.tid];
-          if (si >= 0) {
-            uint32_t rw[4];
-            rng_words(a.seed, gid, (uint32_t)si, 0, 0, attempt, rw);
-            *q_elem(sm, tc, e) = a.init_radius * (2.0f * u01(rw[0]) - 1.0f);
-          }
-        }
-        {
-          float one[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) one[j] = 1.0f;
-          tm_st16(tc, TM_S, one); tm_st16(tc, TM_S + 16, one);
-          ptx::tmem_wait_st();
+#pragma unroll 2
+        for (int d = 0; d < 16; ++d) {
+          float2 v = make_float2(0.f, 0.f);
+          const int s0 = map[(2 * d) * NT], s1 = map[(2 * d + 1) * NT];
+          uint32_t rw[4];
+          if (s0 >= 0) { rng_words(a.seed, gid, (uint32_t)s0, 0, 0, attempt, rw); v.x = a.init_radius * (2.0f * u01(rw[0]) - 1.0f); }
+          if (s1 >= 0) { rng_words(a.seed, gid, (uint32_t)s1, 0, 0, attempt, rw); v.y = a.init_radius * (2.0f * u01(rw[0]) - 1.0f); }
+          *qpair(d) = v;
         }
         ptx::tc_fence_before();
         __syncthreads();
-        eval_point(m, sm, tc, none);
+        eval_point(none);
         int bad = 0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           float g[16];
-          tm_ld16(tc, TM_G + 16 * h, g);
+          tm_ld16(tp, TM_G + 16 * h, g);
 #pragma unroll
           for (int j = 0; j < 16; ++j) bad |= !isfinite(g[j]);
         }
         __syncthreads();
-        if (!isfinite(ctl->U)) bad = 1;
+        if (!isfinite(ctl.U)) bad = 1;
         good = __syncthreads_or(bad) == 0;
       }
-      if (tc.tid == 0) {
-        ChainState& cs = ctl->cs;
+      if (tid == 0) {
+        ChainState& cs = ctl.cs;
         cs.status = good ? 0 : -1;
         cs.eps = 1.0f; cs.da_counter = 0; cs.da_sbar = 0; cs.da_xbar = 0;
         cs.w_counter = 0; cs.w_size = a.w_base_window; cs.w_next = a.w_init_buffer + a.w_base_window - 1; cs.w_nsamp = 0;
         cs.iter = 0; cs.n_leapfrog = 0;
       }
-      // Welford accumulators start at zero
 #pragma unroll 8
-      for (int e = 0; e < EPT; ++e) { wmean[e * NT + tc.tid] = 0.f; wm2[e * NT + tc.tid] = 0.f; }
+      for (int e = 0; e < EPT; ++e) { wmean[e * NT] = 0.f; wm2[e * NT] = 0.f; }
       __syncthreads();
-      const float e0 = find_stepsize(a, sm, tc, ws, gid, 0xFFFFFFFFu, 1.0f);
-      if (tc.tid == 0) { ctl->cs.eps = e0; ctl->cs.da_mu = log(10.0 * (double)e0); }
+      const float e0 = find_stepsize(a, ws, gid, 0xFFFFFFFFu, 1.0f);
+      if (tid == 0) { ctl.cs.eps = e0; ctl.cs.da_mu = log(10.0 * (double)e0); }
       __syncthreads();
     } else {
-      global_to_q(m, sm, tc, qg);
-      global_to_tm(tc, TM_S, sg);
+      global_to_q(qg);
+      global_to_tm(tp, TM_S, sg);
       ptx::tc_fence_before();
       __syncthreads();
     }
 
     // ---- iterations
     for (int it = a.iter_begin; it < a.iter_end; ++it) {
-      const float eps = ctl->cs.eps;
+      const float eps = ctl.cs.eps;
       // outputs of the ENTRY point = draw of iteration it-1 (if it was a sampling iteration)
       Emit em = none;
       const int kprev = it - 1 - a.iter_warmup;
@@ -1152,15 +1187,15 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
         }
       }
       TransStats st;
-      transition(a, sm, tc, ws, gid, (uint32_t)it, eps, em, st);
-      if (tc.tid == 0) {
+      transition(a, ws, gid, (uint32_t)it, eps, em, st);
+      if (tid == 0) {
         float* sp = a.sampler_params + ((size_t)chain * n_iter_total + it) * 8;
         sp[0] = st.lp; sp[1] = st.accept; sp[2] = st.eps; sp[3] = st.depth; sp[4] = st.nleap; sp[5] = st.divergent; sp[6] = st.energy; sp[7] = 0.f;
       }
       if (it < a.iter_warmup) {
         // ---- Stan stepsize_adaptation::learn_stepsize (dual averaging)
-        if (tc.tid == 0) {
-          ChainState& cs = ctl->cs;
+        if (tid == 0) {
+          ChainState& cs = ctl.cs;
           cs.da_counter++;
           const double as = st.accept > 1.f ? 1.0 : (double)st.accept;
           const double eta = 1.0 / (cs.da_counter + 10.0);
@@ -1172,11 +1207,26 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
         }
         __syncthreads();
         // ---- Stan var_adaptation::learn_variance with windowed_adaptation
-        const int wc = ctl->cs.w_counter;
+        const int wc = ctl.cs.w_counter;
         const bool in_window = wc >= a.w_init_buffer && wc < a.iter_warmup - a.w_term_buffer && wc != a.iter_warmup;
-        const bool end_window = wc == ctl->cs.w_next && wc != a.iter_warmup;
-        int nsamp = ctl->cs.w_nsamp;
-        if (in_window) { ++nsamp; welford_add(m, sm, tc, wmean, wm2, nsamp); }
+        const bool end_window = wc == ctl.cs.w_next && wc != a.iter_warmup;
+        int nsamp = ctl.cs.w_nsamp;
+        if (in_window) {  // Welford update, owner layout (padding: q = 0 keeps mean = m2 = 0)
+          ++nsamp;
+          const float inv = 1.0f / (float)nsamp;
+#pragma unroll 4
+          for (int d = 0; d < 16; ++d) {
+            const float2 q = *qpair(d);
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int gi = (2 * d + b) * NT;
+              const float qq = b ? q.y : q.x;
+              const float mu = wmean[gi], dd = qq - mu, mu2 = fmaf(dd, inv, mu);
+              wmean[gi] = mu2;
+              wm2[gi] = fmaf(qq - mu2, dd, wm2[gi]);
+            }
+          }
+        }
         __syncthreads();
         if (end_window) {
           const float n = (float)nsamp;
@@ -1185,20 +1235,20 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
             float s[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int e = h * 16 + j, gi = e * NT + tc.tid;
-              float v = 1.0f;
-              if (elem_valid(m, tc, e)) {
+              const int gi = (h * 16 + j) * NT;
+              float v = 0.f;
+              if (map[gi] >= 0) {
                 const float var = wm2[gi] / (n - 1.0f);
                 v = sqrtf((n / (n + 5.0f)) * var + 1e-3f * (5.0f / (n + 5.0f)));
               }
               s[j] = v;
               wmean[gi] = 0.f; wm2[gi] = 0.f;
             }
-            tm_st16(tc, TM_S + 16 * h, s);
+            tm_st16(tp, TM_S + 16 * h, s);
           }
           ptx::tmem_wait_st();
-          if (tc.tid == 0) {
-            ChainState& cs = ctl->cs;
+          if (tid == 0) {
+            ChainState& cs = ctl.cs;
             const int last = a.iter_warmup - a.w_term_buffer - 1;
             if (cs.w_next != last) {
               cs.w_size *= 2;
@@ -1212,16 +1262,16 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
           nsamp = 0;
           ptx::tc_fence_before();
           __syncthreads();
-          const float e1 = find_stepsize(a, sm, tc, ws, gid, (uint32_t)it, ctl->cs.eps);
-          if (tc.tid == 0) {
-            ChainState& cs = ctl->cs;
+          const float e1 = find_stepsize(a, ws, gid, (uint32_t)it, ctl.cs.eps);
+          if (tid == 0) {
+            ChainState& cs = ctl.cs;
             cs.eps = e1; cs.da_mu = log(10.0 * (double)e1); cs.da_counter = 0; cs.da_sbar = 0; cs.da_xbar = 0;
           }
         }
-        if (tc.tid == 0) {
-          ctl->cs.w_nsamp = nsamp;
-          ctl->cs.w_counter = wc + 1;
-          if (it == a.iter_warmup - 1) ctl->cs.eps = (float)exp(ctl->cs.da_xbar);
+        if (tid == 0) {
+          ctl.cs.w_nsamp = nsamp;
+          ctl.cs.w_counter = wc + 1;
+          if (it == a.iter_warmup - 1) ctl.cs.eps = (float)exp(ctl.cs.da_xbar);
         }
         __syncthreads();
       }
@@ -1236,18 +1286,18 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
           const int slot = kprev / a.keep_every;
           if (slot < a.keep_per_chain) em.draw = a.draws + ((size_t)chain * a.keep_per_chain + slot) * a.draw_len;
         }
-        eval_point(m, sm, tc, em);
+        eval_point(em);
         __syncthreads();
       }
     }
     // ---- persist the chain
-    q_to_global(m, sm, tc, qg);
-    tm_to_global(tc, TM_S, sg);
-    if (tc.tid == 0) { ctl->cs.iter = a.iter_end; a.cs[chain] = ctl->cs; }
+    q_to_global(qg);
+    tm_to_global(tp, TM_S, sg);
+    if (tid == 0) { ctl.cs.iter = a.iter_end; a.cs[chain] = ctl.cs; }
     ptx::tc_fence_before();
     __syncthreads();
   }
-  cta_teardown(sm, tc);
+  cta_teardown();
 }
 
 }  // namespace potus

@@ -43,8 +43,8 @@ constexpr uint32_t TM_S = 384;                  // thread-private: sqrt(inverse 
 // ---- shared-memory map (byte offsets from a 128-aligned base)
 constexpr uint32_t SM_A = 0;
 constexpr uint32_t SM_B = SM_A + 65920;                     // A_REGION rounded to 128
-constexpr uint32_t SM_QZ = SM_B + 2 * B_PLANE;              // float [254][52]
-constexpr uint32_t SM_QNZ = SM_QZ + MAX_T * QZ_PITCH * 4;   // float [NZ_CAP]
+constexpr uint32_t SM_QZ = SM_B + 2 * B_PLANE;              // float [256][52]
+constexpr uint32_t SM_QNZ = SM_QZ + ROWS * QZ_PITCH * 4;    // float [NZ_CAP]   (walk block has 256 rows; 254/255 stay zero)
 constexpr uint32_t SM_GNZ = SM_QNZ + NZ_CAP * 4;            // float [NZ_CAP]   d lp / d theta (data part)
 constexpr uint32_t SM_PK = SM_GNZ + NZ_CAP * 4;             // poll data: 5 x [NPOLL_CAP] 32-bit
 constexpr uint32_t SM_RR = SM_PK + 5 * NPOLL_CAP * 4;       // float [NPOLL_CAP] residuals
@@ -54,7 +54,8 @@ constexpr uint32_t SM_TOT = SM_E + 2 * 256 * 4;             // float [16][52]
 constexpr uint32_t SM_PRIOR = SM_TOT + NWARP * 52 * 4;      // float [64]
 constexpr uint32_t SM_RED = SM_PRIOR + 64 * 4;              // double [16][12]
 constexpr uint32_t SM_CTL = SM_RED + NWARP * 12 * 8;        // control block (scalars), 1024 B
-constexpr uint32_t SM_TOTAL = SM_CTL + 1024;
+constexpr uint32_t SM_MODEL = SM_CTL + 1024;                // ModelDev copy, 512 B
+constexpr uint32_t SM_TOTAL = SM_MODEL + 512;
 static_assert(SM_TOTAL + 128 <= 232448, "shared memory budget (227 KiB) exceeded");
 static_assert(255 * SCR_PITCH * 4 <= A_REGION, "scratch must fit in the operand region");
 
@@ -72,10 +73,11 @@ __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o,
   return (uint32_t)s | ((uint32_t)d << 6) | ((uint32_t)p << 14) | ((uint32_t)m << 24) | ((uint32_t)o << 27) |
          ((uint32_t)un << 30);
 }
-// level-1 task: start[0:16) cnt[16:24) type[24:32)   (type 0 contiguous, 1 contiguous*unadjusted, 2 id list)
+// level-1 task: x = start[0:16) cnt[16:24) type[24:32), y = psum slot   (type 0 contiguous, 1 contiguous*unadjusted, 2 id list);
+// sorted by decreasing length so that the threads of a warp get similar work
 // level-2 final: word0 = pstart[0:16) pcnt[16:24) kind[24:32); word1 = destination index
 //   kind 0: A2[t][s] operand cell (dest = t*64+s, scaled by scale_G); kind 1: gnz[dest] (scaled by sigma_c);
-//   kind 2: ebar[dest] (g_e, unscaled)
+//   kind 2: ebar[dest] (g_e, unscaled); kind 3: like kind 0 but summing residuals rr[pstart..pstart+pcnt) directly (poll cells)
 
 struct ModelDev {
   int S, T, P, M, Pop, Nn, Ns, N, full, D, NZ, npair;
@@ -88,7 +90,7 @@ struct ModelDev {
   const void* btiles;       // 2 x B_PLANE bytes: X hi, X lo  (X[s][k] = 256*L0[s][k]; row 51 = 256*L0^T w)
   const uint32_t* pk;       // 5 x NPOLL_CAP words: idx, n, eta_hat, p_hat, rho_hat
   const float* prior;       // [64] mu_b_prior, [51] = w . prior
-  const uint32_t* t1;       // [n_t1]
+  const uint2* t1;          // [n_t1]  x = start|cnt<<16|type<<24, y = psum slot
   const uint2* t2;          // [n_t2]
   const uint16_t* ids;      // id lists of the type-2 tasks
   const int32_t* map_i2s;   // [VEC] internal slot -> Stan unconstrained index (-1 = padding)
@@ -132,5 +134,7 @@ struct EvalArgs {      // test hook: lp/grad for n vectors
   double* u_out;       // [n]
   float* mu_out;       // optional [n][S*T] (mu_b, Stan column-major) or null
 };
+
+static_assert(sizeof(ModelDev) <= 512, "ModelDev must fit its shared-memory slot");
 
 }  // namespace potus

@@ -145,6 +145,32 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       : "memory");
 }
 
+
+// float-typed variants (no integer<->float register moves around the asm)
+#define PTX_RF16(v, o) \
+  "=f"(v[o + 0]), "=f"(v[o + 1]), "=f"(v[o + 2]), "=f"(v[o + 3]), "=f"(v[o + 4]), "=f"(v[o + 5]), "=f"(v[o + 6]), \
+      "=f"(v[o + 7]), "=f"(v[o + 8]), "=f"(v[o + 9]), "=f"(v[o + 10]), "=f"(v[o + 11]), "=f"(v[o + 12]), "=f"(v[o + 13]), \
+      "=f"(v[o + 14]), "=f"(v[o + 15])
+#define PTX_WF16(v, o) \
+  "f"(v[o + 0]), "f"(v[o + 1]), "f"(v[o + 2]), "f"(v[o + 3]), "f"(v[o + 4]), "f"(v[o + 5]), "f"(v[o + 6]), "f"(v[o + 7]), \
+      "f"(v[o + 8]), "f"(v[o + 9]), "f"(v[o + 10]), "f"(v[o + 11]), "f"(v[o + 12]), "f"(v[o + 13]), "f"(v[o + 14]), \
+      "f"(v[o + 15])
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : PTX_RF16(v, 0)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      PTX_WF16(v, 0)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
 // x*scale ~= hi + lo * 2^-11, 22 significant bits.
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
