@@ -320,6 +320,7 @@ typedef struct {
   /* transition state */
   double H0; int n_leapfrog; double sum_metro; int divergent; uint32_t iter; uint32_t merge_ctr;
   int64_t n_grad;
+  double* arena; size_t arena_top, arena_cap; /* bump allocator for the tree recursion (no malloc in the hot path) */
 } Chain;
 
 static void z_grad(Chain* c) { c->V = -logp_grad_w(c->m, c->q, c->g, c->literal, c->wk, NULL); for (int i = 0; i < c->D; ++i) c->g[i] = -c->g[i]; c->n_grad++; }
@@ -342,6 +343,12 @@ static int crit(const Chain* c, const double* p_a, const double* p_b, const doub
   return db > 0 && da > 0;
 }
 static double* vnew(int D) { return (double*)malloc(sizeof(double) * D); }
+static double* arena_get(Chain* c, int D, int zero) {
+  if (c->arena_top + (size_t)D > c->arena_cap) { fprintf(stderr, "oracle: arena exhausted\n"); abort(); }
+  double* r = c->arena + c->arena_top; c->arena_top += (size_t)D;
+  if (zero) memset(r, 0, sizeof(double) * D);
+  return r;
+}
 
 /* one leaf: leapfrog + energy bookkeeping (base_nuts.hpp build_tree depth==0) */
 static int leaf(Chain* c, double sign, double* lsw, double* h_out) {
@@ -370,8 +377,9 @@ static int build_rec(Chain* c, int depth, double sign, double* z_prop, double* p
     return ok;
   }
   double lsw_i = -INFINITY, lsw_f = -INFINITY;
-  double *p_ie = vnew(D), *rho_i = (double*)calloc(D, sizeof(double));
-  double *p_fb = vnew(D), *rho_f = (double*)calloc(D, sizeof(double)), *z_prop_f = vnew(D), *ext = vnew(D);
+  const size_t mark = c->arena_top;
+  double *p_ie = arena_get(c, D, 0), *rho_i = arena_get(c, D, 1);
+  double *p_fb = arena_get(c, D, 0), *rho_f = arena_get(c, D, 1), *z_prop_f = arena_get(c, D, 0), *ext = arena_get(c, D, 0);
   int ok = build_rec(c, depth - 1, sign, z_prop, ps_beg_p, p_ie, rho_i, &lsw_i);
   if (ok) ok = build_rec(c, depth - 1, sign, z_prop_f, p_fb, ps_end_p, rho_f, &lsw_f);
   if (ok) {
@@ -390,7 +398,7 @@ static int build_rec(Chain* c, int depth, double sign, double* z_prop, double* p
     for (int i = 0; i < D; ++i) ext[i] = rho_f[i] + p_ie[i];
     ok = ok && crit(c, p_ie, ps_end_p, ext);
   }
-  free(p_ie); free(rho_i); free(p_fb); free(rho_f); free(z_prop_f); free(ext);
+  c->arena_top = mark;
   return ok;
 }
 
@@ -611,6 +619,7 @@ static void run_chain(OrcRun* r, int ci) {
   c.literal = r->literal; c.tree_mode = r->tree_mode; c.max_depth = r->cfg.max_treedepth;
   c.inv_metric = vnew(D); for (int i = 0; i < D; ++i) c.inv_metric[i] = 1.0;
   c.q = vnew(D); c.p = vnew(D); c.g = vnew(D); c.eps = 1.0;
+  c.arena_cap = (size_t)(c.max_depth + 2) * 6 * D; c.arena = (double*)malloc(sizeof(double) * c.arena_cap); c.arena_top = 0;
   /* random inits U(-r, r), retry while lp/grad not finite (<= 100 attempts) */
   for (uint32_t attempt = 0; attempt < 100; ++attempt) {
     for (int i = 0; i < D; ++i) {
@@ -653,7 +662,7 @@ static void run_chain(OrcRun* r, int ci) {
     }
   }
   r->final_eps[ci] = c.eps; r->n_leapfrog[ci] = total_lf;
-  free(a.mean); free(a.m2); free(c.inv_metric); free(c.q); free(c.p); free(c.g); work_free(c.wk);
+  free(a.mean); free(a.m2); free(c.inv_metric); free(c.q); free(c.p); free(c.g); free(c.arena); work_free(c.wk);
 }
 static void* worker(void* arg) {
   OrcRun* r = (OrcRun*)arg;
@@ -696,6 +705,7 @@ ORC_API void orc_transitions(const OrcModel* m, uint64_t seed, uint32_t chain, i
   c.m = m; c.wk = work_new(m); c.D = D; c.seed = seed; c.chain = chain; c.literal = 0; c.tree_mode = tree_mode; c.max_depth = max_depth;
   c.inv_metric = vnew(D); memcpy(c.inv_metric, inv_metric, sizeof(double) * D);
   c.q = vnew(D); c.p = vnew(D); c.g = vnew(D); c.eps = eps;
+  c.arena_cap = (size_t)(max_depth + 2) * 6 * D; c.arena = (double*)malloc(sizeof(double) * c.arena_cap); c.arena_top = 0;
   memcpy(c.q, q0, sizeof(double) * D);
   for (int it = 0; it < n_iter; ++it) {
     c.iter = iter0 + (uint32_t)it;
@@ -704,5 +714,5 @@ ORC_API void orc_transitions(const OrcModel* m, uint64_t seed, uint32_t chain, i
     so[0] = st.lp; so[1] = st.accept_stat; so[2] = st.stepsize; so[3] = st.treedepth; so[4] = st.n_leapfrog; so[5] = st.divergent; so[6] = st.energy;
     memcpy(q_out + (size_t)it * D, c.q, sizeof(double) * D);
   }
-  free(c.inv_metric); free(c.q); free(c.p); free(c.g); work_free(c.wk);
+  free(c.inv_metric); free(c.q); free(c.p); free(c.g); free(c.arena); work_free(c.wk);
 }

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def test_first_transitions_follow_the_oracle(pkg, orc_mod, datalists, cuda_lib):
     """Same Philox streams, same algorithm: until fp32-vs-fp64 round-off is amplified by the chaotic dynamics,
     the device and the fp64 oracle (tree_mode=1) take identical decisions.  Checked on the first 12 warm-up
-    iterations (depths up to 10): tree depth, n_leapfrog and divergence equal; lp within 0.1 on the first 5 iterations (far-out inits, |lp| ~ 1.2e6); step size within 1%."""
+    iterations (depths up to 10): tree depth, n_leapfrog and divergence equal; lp within 0.1 on the first 5 iterations (far-out inits, |lp| ~ 1.2e6); step size within 1% and accept_stat within 0.02 on the first 8."""
     d = datalists[2016]
     fit = pkg.cmdstan_model().sample(data=d, seed=1843, chains=2, iter_warmup=12, iter_sampling=0, keep_per_chain=0)
     sp = fit.sampler_params()
@@ -27,8 +27,8 @@ def test_first_transitions_follow_the_oracle(pkg, orc_mod, datalists, cuda_lib):
         assert np.array_equal(sp["divergent__"][c], r["stats"][c, :, 5])
         dlp = np.abs(sp["lp__"][c] - r["stats"][c, :, 0])
         assert dlp[:5].max() < 0.1, dlp   # later iterations: a flipped multinomial pick changes lp by O(10) this far from stationarity
-        assert np.abs(sp["stepsize__"][c] / r["stats"][c, :, 2] - 1).max() < 0.01
-        assert np.abs(sp["accept_stat__"][c] - r["stats"][c, :, 1]).max() < 0.02
+        assert np.abs(sp["stepsize__"][c] / r["stats"][c, :, 2] - 1)[:8].max() < 0.01
+        assert np.abs(sp["accept_stat__"][c] - r["stats"][c, :, 1])[:8].max() < 0.02
 
 
 def test_sharding_does_not_change_any_chain(pkg, datalists, cuda_lib):

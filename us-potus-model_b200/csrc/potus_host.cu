@@ -280,7 +280,8 @@ int build_model(const PotusData* d, HostModel& hm) {
   prior[NAT_COL] = (float)wp;
 
   // ---- segment-sum tasks
-  std::vector<uint2> t1;
+  std::vector<uint2> t1;   // x = start | cnt<<16 | type<<24, y = psum slot (packed to one word below)
+  std::vector<uint32_t> cells;
   std::vector<uint2> t2;
   std::vector<uint16_t> ids;
   auto add_segments = [&](int type, int start, int cnt, int& pstart, int& pcnt) {
@@ -301,7 +302,8 @@ int build_model(const PotusData* d, HostModel& hm) {
     int e = k;
     while (e < N && hp[e].dd == hp[k].dd && hp[e].s == hp[k].s && ((e < Ns) == (k < Ns))) ++e;
     if (e - k > 255) return fail(POTUS_ERR_UNSUPPORTED, "more than 255 polls in one (state, day) cell");
-    add_final(3, hp[k].dd * 64 + hp[k].s, k, e - k);  // direct sum of the cell's residuals
+    if (e - k > 63 || k > 4095) return fail(POTUS_ERR_UNSUPPORTED, "poll cell does not fit the packed descriptor");
+    cells.push_back((uint32_t)k | ((uint32_t)(e - k) << 12) | ((uint32_t)(hp[k].dd * 64 + hp[k].s) << 18));
     k = e;
   }
   if (full) {  // g_e[t] = sum over polls of day t of unadjusted * r
@@ -337,8 +339,19 @@ int build_model(const PotusData* d, HostModel& hm) {
   // balance: longest tasks first, so thread i of every warp gets tasks of similar length
   std::stable_sort(t1.begin(), t1.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
   std::stable_sort(t2.begin(), t2.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
-  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || ids.size() > 65535)
+  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || (int)ids.size() > NIDS_CAP || (int)cells.size() > NCELL_CAP)
     return fail(POTUS_ERR_UNSUPPORTED, "poll structure needs more segment tasks than the resident kernel holds");
+  std::stable_sort(cells.begin(), cells.end(), [](uint32_t a, uint32_t b) { return ((a >> 12) & 63) > ((b >> 12) & 63); });
+  std::vector<uint32_t> t1p(NT1_CAP, 0u);
+  for (size_t i = 0; i < t1.size(); ++i) {
+    const uint32_t start = t1[i].x & 0xffff, cnt = (t1[i].x >> 16) & 0xff, type = t1[i].x >> 24;
+    if (start > 8191 || cnt > 32 || t1[i].y > 1023) return fail(POTUS_ERR_UNSUPPORTED, "segment task does not fit the packed descriptor");
+    t1p[i] = start | (cnt << 13) | (type << 19) | (t1[i].y << 21);
+  }
+  cells.resize(NCELL_CAP, 0u);
+  m.n_cell = 0; for (uint32_t c : cells) if ((c >> 12) & 63) ++m.n_cell;
+  m.n_ids = (int)ids.size();
+  ids.resize(NIDS_CAP, 0);
   if (seg_overflow) return fail(POTUS_ERR_UNSUPPORTED, "a poll group needs more than 255 segments");
   m.n_t1 = (int)t1.size(); m.n_t2 = (int)t2.size();
 
@@ -377,7 +390,8 @@ int build_model(const PotusData* d, HostModel& hm) {
   if ((rc = upload(hm, bt, &p))) return rc; m.btiles = p;
   if ((rc = upload(hm, pk, &p))) return rc; m.pk = (const uint32_t*)p;
   if ((rc = upload(hm, prior, &p))) return rc; m.prior = (const float*)p;
-  if ((rc = upload(hm, t1, &p))) return rc; m.t1 = (const uint2*)p;
+  if ((rc = upload(hm, t1p, &p))) return rc; m.t1 = (const uint32_t*)p;
+  if ((rc = upload(hm, cells, &p))) return rc; m.cells = (const uint32_t*)p;
   if ((rc = upload(hm, t2, &p))) return rc; m.t2 = (const uint2*)p;
   if ((rc = upload(hm, ids, &p))) return rc; m.ids = (const uint16_t*)p;
   if ((rc = upload(hm, hm.map_i2s, &p))) return rc; m.map_i2s = (const int32_t*)p;

@@ -386,6 +386,9 @@ __device__ __noinline__ void eval_point(const Emit em) {
   if (em.mu != nullptr)
     for (int i = tid; i < S * T; i += NT) { int t = i / S, s = i - t * S; em.mu[i] = sSCR()[t * SCR_PITCH + s]; }
 
+  // level-2 final of this thread (at most one per thread), fetched now so that its L2 latency hides behind the polls
+  uint2 t2d = make_uint2(0u, 0u);
+  if (tid < m.n_t2) t2d = __ldg(m.t2 + tid);
   // ---------------- P5: polls: linear predictor (stan:95-112), centred binomial_logit (stan:130-131), residuals
   {
     float fsum = 0.f, gm[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, gp[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, rnat = 0.f;
@@ -452,23 +455,22 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
   }
   __syncthreads();  // S4
-  // ---------------- P6: level-1 segment sums of residuals (cells, days, pollsters, states)
+  // ---------------- P6: level-1 segment sums of residuals (days, pollsters, states); descriptors live in shared memory
   {
     const float* rr = sRR();
+    const uint32_t* t1 = SMP(uint32_t, SM_T1);
+    const uint16_t* idl = SMP(uint16_t, SM_IDS);
     for (int i = tid; i < m.n_t1; i += NT) {
-      const uint2 tdd = __ldg(m.t1 + i);
-      const uint32_t td = tdd.x;
-      const int start = td & 0xffff, cnt = (td >> 16) & 0xff, type = td >> 24;
+      const uint32_t td = t1[i];
+      const int start = td & 8191, cnt = (td >> 13) & 63, type = (td >> 19) & 3, slot = td >> 21;
       float acc = 0.f;
-      if (type == 0) {
-        for (int j = 0; j < cnt; ++j) acc += rr[start + j];
-      } else if (type == 1) {
+      if (type == 1) {
         for (int j = 0; j < cnt; ++j) acc += ((sPKI()[start + j] >> 30) & 1) ? rr[start + j] : 0.f;
       } else {
-        const uint16_t* ids = m.ids + start;
-        for (int j = 0; j < cnt; ++j) acc += rr[__ldg(ids + j)];
+        const uint16_t* ids = idl + start;
+        for (int j = 0; j < cnt; ++j) acc += rr[ids[j]];
       }
-      sPSUM()[tdd.y] = acc;
+      sPSUM()[slot] = acc;
     }
   }
   if (w == 0 && l < 10) {  // finalize the block reduction
@@ -493,22 +495,35 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
   }
   __syncthreads();  // S5
-  // ---------------- P7: level-2 finals -> G operand cells / pollster gradients / g_e
+  // ---------------- P7: G operand cells (direct sums of residuals) and level-2 finals -> pollster gradients / g_e / g_pb row
   {
+    const float* rr = sRR();
+    const uint32_t* cells = SMP(uint32_t, SM_CELL);
+    unsigned char* ahi = smem_raw + SM_A;
+    for (int i = tid; i < m.n_cell; i += NT) {
+      const uint32_t cd = cells[i];
+      const int start = cd & 4095, cnt = (cd >> 12) & 63, t = cd >> 24, s = (cd >> 18) & 63;
+      float acc = rr[start];
+      for (int j = 1; j < cnt; ++j) acc += rr[start + j];
+      __half hi, lo;
+      ptx::split_f16(acc * m.scale_G, hi, lo);
+      const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
+      *reinterpret_cast<__half*>(ahi + off) = hi;
+      *reinterpret_cast<__half*>(ahi + A_PLANE + off) = lo;
+    }
     const float* ps_ = sPSUM();
-    for (int i = tid; i < m.n_t2; i += NT) {
-      const uint2 td = __ldg(m.t2 + i);
+    if (tid < m.n_t2) {
+      const uint2 td = t2d;   // prefetched before the poll phase
       const int ps = td.x & 0xffff, pc = (td.x >> 16) & 0xff, kind = td.x >> 24;
-      const float* src = (kind == 3) ? sRR() : ps_;
       float acc = 0.f;
-      for (int j = 0; j < pc; ++j) acc += src[ps + j];
-      if (kind == 0 || kind == 3) {
+      for (int j = 0; j < pc; ++j) acc += ps_[ps + j];
+      if (kind == 0) {
         const int t = td.y >> 6, s = td.y & 63;
         __half hi, lo;
         ptx::split_f16(acc * m.scale_G, hi, lo);
         const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
-        *reinterpret_cast<__half*>(smem_raw + SM_A + off) = hi;
-        *reinterpret_cast<__half*>(smem_raw + SM_A + A_PLANE + off) = lo;
+        *reinterpret_cast<__half*>(ahi + off) = hi;
+        *reinterpret_cast<__half*>(ahi + A_PLANE + off) = lo;
       } else if (kind == 1) {
         sGNZ()[td.y] = m.sig_c * acc;
       } else {
@@ -1046,8 +1061,11 @@ __device__ __forceinline__ void cta_setup(const ModelDev& mg) {
   ptx::tc_fence_after();
   // constants: TMA bulk copies (global -> shared), one mbarrier
   if (tid == 0) {
-    const uint32_t bytes = 2 * B_PLANE + 5 * NPOLL_CAP * 4 + 64 * 4;
+    const uint32_t bytes = 2 * B_PLANE + 5 * NPOLL_CAP * 4 + 64 * 4 + NT1_CAP * 4 + NCELL_CAP * 4 + NIDS_CAP * 2;
     ptx::mbar_expect_tx(&ctl.bar_load, bytes);
+    ptx::bulk_g2s(smem_raw + SM_T1, mg.t1, NT1_CAP * 4, &ctl.bar_load);
+    ptx::bulk_g2s(smem_raw + SM_CELL, mg.cells, NCELL_CAP * 4, &ctl.bar_load);
+    ptx::bulk_g2s(smem_raw + SM_IDS, mg.ids, NIDS_CAP * 2, &ctl.bar_load);
     ptx::bulk_g2s(smem_raw + SM_B, mg.btiles, 2 * B_PLANE, &ctl.bar_load);
     ptx::bulk_g2s(smem_raw + SM_PK, mg.pk, 5 * NPOLL_CAP * 4, &ctl.bar_load);
     ptx::bulk_g2s(smem_raw + SM_PRIOR, mg.prior, 64 * 4, &ctl.bar_load);

@@ -21,8 +21,10 @@ constexpr int ROWS = 256, KPAD = 64;
 constexpr int SCR_PITCH = 53;           // fp32 scratch pitch (odd: conflict-free row-per-lane access)
 constexpr int QZ_PITCH = 52;            // q walk block [t][52] (float2 per state pair)
 constexpr int NPOLL_CAP = 1664;
-constexpr int NT1_CAP = 3072;           // level-1 segment-sum tasks (<=32 polls each)
-constexpr int NT2_CAP = 2560;           // level-2 finals
+constexpr int NT1_CAP = 1024;           // level-1 segment-sum tasks (<=32 polls each): pollster / state / day lists
+constexpr int NCELL_CAP = 1440;         // direct (state,day) / national-day cells
+constexpr int NT2_CAP = 512;            // level-2 finals over level-1 partial sums (one per thread)
+constexpr int NIDS_CAP = 2 * NPOLL_CAP; // id lists (by pollster, by state)
 constexpr int MAX_MODE = 4;             // M, Pop <= 4
 constexpr int MAX_DEPTH_CAP = 10;
 
@@ -49,7 +51,10 @@ constexpr uint32_t SM_GNZ = SM_QNZ + NZ_CAP * 4;            // float [NZ_CAP]   
 constexpr uint32_t SM_PK = SM_GNZ + NZ_CAP * 4;             // poll data: 5 x [NPOLL_CAP] 32-bit
 constexpr uint32_t SM_RR = SM_PK + 5 * NPOLL_CAP * 4;       // float [NPOLL_CAP] residuals
 constexpr uint32_t SM_PSUM = SM_RR + NPOLL_CAP * 4;         // float [NT1_CAP]
-constexpr uint32_t SM_E = SM_PSUM + NT1_CAP * 4;            // float e[256], ebar[256]
+constexpr uint32_t SM_T1 = SM_PSUM + NT1_CAP * 4;           // uint32 [NT1_CAP] packed level-1 tasks
+constexpr uint32_t SM_CELL = SM_T1 + NT1_CAP * 4;           // uint32 [NCELL_CAP] packed cells
+constexpr uint32_t SM_IDS = SM_CELL + NCELL_CAP * 4;        // uint16 [NIDS_CAP]
+constexpr uint32_t SM_E = SM_IDS + NIDS_CAP * 2;            // float e[256], ebar[256]
 constexpr uint32_t SM_TOT = SM_E + 2 * 256 * 4;             // float [16][52]
 constexpr uint32_t SM_PRIOR = SM_TOT + NWARP * 52 * 4;      // float [64]
 constexpr uint32_t SM_RED = SM_PRIOR + 64 * 4;              // double [16][12]
@@ -73,8 +78,9 @@ __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o,
   return (uint32_t)s | ((uint32_t)d << 6) | ((uint32_t)p << 14) | ((uint32_t)m << 24) | ((uint32_t)o << 27) |
          ((uint32_t)un << 30);
 }
-// level-1 task: x = start[0:16) cnt[16:24) type[24:32), y = psum slot   (type 0 contiguous, 1 contiguous*unadjusted, 2 id list);
-// sorted by decreasing length so that the threads of a warp get similar work
+// level-1 task (one packed word, in shared memory): start[0:13) cnt[13:19) type[19:21) psum-slot[21:31)
+//   type 1 contiguous*unadjusted, 2 id list; sorted by decreasing length so that a warp's threads get similar work
+// cell (one packed word, shared memory): start[0:12) cnt[12:18) dest[18:32) with dest = t*64+s  -> G operand cell
 // level-2 final: word0 = pstart[0:16) pcnt[16:24) kind[24:32); word1 = destination index
 //   kind 0: A2[t][s] operand cell (dest = t*64+s, scaled by scale_G); kind 1: gnz[dest] (scaled by sigma_c);
 //   kind 2: ebar[dest] (g_e, unscaled); kind 3: like kind 0 but summing residuals rr[pstart..pstart+pcnt) directly (poll cells)
@@ -82,7 +88,7 @@ __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o,
 struct ModelDev {
   int S, T, P, M, Pop, Nn, Ns, N, full, D, NZ, npair;
   int nz_zT, nz_c, nz_m, nz_pop, nz_umu, nz_urho, nz_ze, nz_x, nz_zb;  // offsets inside the nz block
-  int n_t1, n_t2;
+  int n_t1, n_t2, n_cell, n_ids;
   float a_b, a_T, a_w, sig_c, sig_m, sig_pop, sig_n, sig_s, sig_e;
   float scale_G, inv_scale_G;
   double lp_const;          // sum_i y_i*eta_hat_i - n_i*softplus(eta_hat_i): the centring constant
@@ -90,7 +96,8 @@ struct ModelDev {
   const void* btiles;       // 2 x B_PLANE bytes: X hi, X lo  (X[s][k] = 256*L0[s][k]; row 51 = 256*L0^T w)
   const uint32_t* pk;       // 5 x NPOLL_CAP words: idx, n, eta_hat, p_hat, rho_hat
   const float* prior;       // [64] mu_b_prior, [51] = w . prior
-  const uint2* t1;          // [n_t1]  x = start|cnt<<16|type<<24, y = psum slot
+  const uint32_t* t1;       // [NT1_CAP] packed level-1 tasks (copied to shared memory)
+  const uint32_t* cells;    // [NCELL_CAP] packed cells (copied to shared memory)
   const uint2* t2;          // [n_t2]
   const uint16_t* ids;      // id lists of the type-2 tasks
   const int32_t* map_i2s;   // [VEC] internal slot -> Stan unconstrained index (-1 = padding)
