@@ -29,6 +29,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_prof() -> str:
+    """Development build with per-phase clock64 counters (-DPOTUS_PROF); never used by tests or bench."""
+    os.makedirs(LIB_DIR, exist_ok=True)
+    out = os.path.join(LIB_DIR, "libpotus_b200_prof.so")
+    res = subprocess.run([_nvcc(), *NVCC_FLAGS, "-DPOTUS_PROF", "-o", out, os.path.join(CSRC, "potus_lib.cu")], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

@@ -287,7 +287,7 @@ int build_model(const PotusData* d, HostModel& hm) {
   auto add_segments = [&](int type, int start, int cnt, int& pstart, int& pcnt) {
     pstart = (int)t1.size(); pcnt = 0;
     while (cnt > 0) {
-      int c = std::min(cnt, 32);
+      int c = std::min(cnt, (int)SEG);
       t1.push_back(make_uint2((uint32_t)start | ((uint32_t)c << 16) | ((uint32_t)type << 24), (uint32_t)t1.size()));
       start += c; cnt -= c; ++pcnt;
     }
@@ -339,14 +339,14 @@ int build_model(const PotusData* d, HostModel& hm) {
   // balance: longest tasks first, so thread i of every warp gets tasks of similar length
   std::stable_sort(t1.begin(), t1.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
   std::stable_sort(t2.begin(), t2.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
-  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || (int)ids.size() > NIDS_CAP || (int)cells.size() > NCELL_CAP)
+  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || (int)t2.size() > NT || (int)ids.size() > NIDS_CAP || (int)cells.size() > NCELL_CAP)
     return fail(POTUS_ERR_UNSUPPORTED, "poll structure needs more segment tasks than the resident kernel holds");
   std::stable_sort(cells.begin(), cells.end(), [](uint32_t a, uint32_t b) { return ((a >> 12) & 63) > ((b >> 12) & 63); });
   std::vector<uint32_t> t1p(NT1_CAP, 0u);
   for (size_t i = 0; i < t1.size(); ++i) {
     const uint32_t start = t1[i].x & 0xffff, cnt = (t1[i].x >> 16) & 0xff, type = t1[i].x >> 24;
-    if (start > 8191 || cnt > 32 || t1[i].y > 1023) return fail(POTUS_ERR_UNSUPPORTED, "segment task does not fit the packed descriptor");
-    t1p[i] = start | (cnt << 13) | (type << 19) | (t1[i].y << 21);
+    if (start > 8191 || cnt > SEG || t1[i].y > 4095) return fail(POTUS_ERR_UNSUPPORTED, "segment task does not fit the packed descriptor");
+    t1p[i] = start | (cnt << 13) | (type << 18) | (t1[i].y << 20);
   }
   cells.resize(NCELL_CAP, 0u);
   m.n_cell = 0; for (uint32_t c : cells) if ((c >> 12) & 63) ++m.n_cell;
@@ -362,7 +362,7 @@ int build_model(const PotusData* d, HostModel& hm) {
     for (int e = 0; e < EPT; ++e) {
       int idx = -1;
       if (l < ZLANES) {
-        int s = 2 * l + (e & 1), t = 16 * wq + (e >> 1);
+        int s = 2 * l + (e & 1), t = DPW * wq + (e >> 1);
         if (s < S && t < T) idx = o.Z + s + S * t;
       } else {
         int k = (wq * NZ_LANES + (l - ZLANES)) * EPT + e;
@@ -428,6 +428,7 @@ struct PotusSampler {
   ChainState* cs = nullptr;
   int* queue = nullptr;
   float *draws = nullptr, *monitor = nullptr, *sparams = nullptr;
+  unsigned long long* prof = nullptr;  // phase cycle counters (POTUS_PROF development builds)
   bool ran = false;
   PotusStats stats{};
   std::vector<float> h_draws, h_monitor, h_sparams;
@@ -450,7 +451,7 @@ void potus_destroy(PotusSampler* s) {
   if (!s) return;
   free_model(s->hm);
   cudaFree(s->q); cudaFree(s->sqrt_m); cudaFree(s->wf_mean); cudaFree(s->wf_m2); cudaFree(s->workspace);
-  cudaFree(s->cs); cudaFree(s->queue); cudaFree(s->draws); cudaFree(s->monitor); cudaFree(s->sparams);
+  cudaFree(s->cs); cudaFree(s->queue); cudaFree(s->draws); cudaFree(s->monitor); cudaFree(s->sparams); cudaFree(s->prof);
   delete s;
 }
 
@@ -491,7 +492,7 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
       (rc = alloc((void**)&s->cs, (size_t)C * sizeof(ChainState))) || (rc = alloc((void**)&s->queue, sizeof(int))) ||
       (rc = alloc((void**)&s->draws, (size_t)C * s->keep * s->draw_len * sizeof(float))) ||
       (rc = alloc((void**)&s->monitor, (size_t)C * config->iter_sampling * (m.S + 1) * sizeof(float))) ||
-      (rc = alloc((void**)&s->sparams, (size_t)C * n_it * 8 * sizeof(float)))) {
+      (rc = alloc((void**)&s->sparams, (size_t)C * n_it * 8 * sizeof(float))) || (rc = alloc((void**)&s->prof, 64 * sizeof(unsigned long long)))) {
     potus_destroy(s);
     return rc;
   }
@@ -516,6 +517,7 @@ static RunArgs make_args(PotusSampler* s, int it0, int it1, int do_init) {
   a.seed = s->cfg.seed; a.adapt_delta = (float)s->cfg.adapt_delta; a.init_radius = (float)s->cfg.init_radius;
   a.q = s->q; a.sqrt_m = s->sqrt_m; a.wf_mean = s->wf_mean; a.wf_m2 = s->wf_m2; a.cs = s->cs; a.workspace = s->workspace;
   a.queue = s->queue; a.draws = s->draws; a.monitor = s->monitor; a.sampler_params = s->sparams;
+  a.prof = s->prof;
   return a;
 }
 
@@ -571,6 +573,16 @@ int potus_run(PotusSampler* s) {
   st.gpu_launches = launches;
   st.seconds_warmup = ms01 * 1e-3; st.seconds_sampling = ms12 * 1e-3; st.seconds_total = (ms01 + ms12) * 1e-3;
   st.n_params = s->hm.m.D; st.n_draws_kept = C * s->keep;
+#ifdef POTUS_PROF
+  {
+    unsigned long long hp[64];
+    if (cudaMemcpy(hp, s->prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "[potus_prof] leaves=%llu cycles/leaf per phase (thread 0, summed over CTAs):", hp[39]);
+      for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%.0f", i, hp[39] ? (double)hp[i] / (double)hp[39] : 0.0);
+      fprintf(stderr, "\n");
+    }
+  }
+#endif
   s->ran = true; s->have_host = false;
   return POTUS_OK;
 }

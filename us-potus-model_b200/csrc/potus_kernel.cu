@@ -35,13 +35,29 @@ struct Ctl {
   float rho, mu_e, sig_rho, rho_term;  // rho_term = sig_e*rho/sqrt(1-rho^2)
   float rn_total;
   float pad0;
-  alignas(16) float kred[2][16];
-  alignas(16) float mred[16][8];
+  alignas(16) float kred[2][NWARP];
+  alignas(16) float mred[NWARP][8];
   ChainState cs;
+#ifdef POTUS_PROF
+  unsigned long long prof[40];
+#endif
 };
-static_assert(sizeof(Ctl) <= 1024, "control block");
+static_assert(sizeof(Ctl) <= 2048, "control block");
+static_assert(NT == 512 && EPT == 32 && DPW == 16, "this file is written for 16 warps x 32 elements");
 
 #define SMP(T_, off) (reinterpret_cast<T_*>(smem_raw + (off)))
+// optional phase clocks (development builds, -DPOTUS_PROF): thread 0 accumulates cycles per phase
+#ifdef POTUS_PROF
+#define PROF_DECL long long prof_t_ = clock64()
+#define PROF(i) do { if (threadIdx.x == 0) { long long n_ = clock64(); CTL().prof[i] += (unsigned long long)(n_ - prof_t_); prof_t_ = n_; } } while (0)
+#define PROF_RESET prof_t_ = clock64()
+#define PROF_COUNT CTL().prof[39] += 1
+#else
+#define PROF_DECL
+#define PROF(i)
+#define PROF_RESET
+#define PROF_COUNT
+#endif
 __device__ __forceinline__ const ModelDev& MD() { return *SMP(const ModelDev, SM_MODEL); }
 __device__ __forceinline__ Ctl& CTL() { return *SMP(Ctl, SM_CTL); }
 __device__ __forceinline__ float* sQZ() { return SMP(float, SM_QZ); }
@@ -105,6 +121,8 @@ __device__ __forceinline__ void tm_ld16(uint32_t tp, uint32_t col, float (&v)[16
   ptx::tmem_wait_ld();
 }
 __device__ __forceinline__ void tm_st16(uint32_t tp, uint32_t col, const float (&v)[16]) { ptx::tmem_st16f(tp + col, v); }
+// issue-only variants: several loads share one tcgen05.wait::ld (each ld+wait round trip costs a few hundred cycles)
+__device__ __forceinline__ void tm_ld16_nowait(uint32_t tp, uint32_t col, float (&v)[16]) { ptx::tmem_ld16f(tp + col, v); }
 __device__ __forceinline__ float* slot_ptr(float* ws, int slot) { return ws + (size_t)slot * VEC; }
 
 __device__ __forceinline__ void tm_to_global(uint32_t tp, uint32_t col, float* g) {
@@ -252,6 +270,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
   const int nd = min(max(T - 16 * w, 0), 16);       // day rows of this warp that exist
   const int ndw = min(max(T - 1 - 16 * w, 0), 16);  // ... that carry a walk innovation (t <= T-2)
   float qsq = 0.f;
+  PROF_DECL;
 
   // ---------------- P1: reverse scan of the walk innovations (poll_model_2020.stan:86 collapsed)
   float c[32];
@@ -279,14 +298,16 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
   }
   __syncthreads();  // S1
+  PROF(0);
   // ---------------- P2: W -> fp16 hi/lo operand planes (K-major, SWIZZLE_NONE)
   {
     float carry0 = 0.f, carry1 = 0.f, zt0 = 0.f, zt1 = 0.f, zb0 = 0.f, zb1 = 0.f;
     const bool act = l < m.npair;
     if (act) {
-      for (int w2 = w + 1; w2 < NWARP; ++w2) {
+#pragma unroll
+      for (int w2 = 1; w2 < NWARP; ++w2) {   // fixed trip count: all loads issue back to back
         const float2 t2 = *reinterpret_cast<const float2*>(sTOT() + w2 * 52 + 2 * l);
-        carry0 += t2.x; carry1 += t2.y;
+        if (w2 > w) { carry0 += t2.x; carry1 += t2.y; }
       }
       zt0 = sQNZ()[m.nz_zT + 2 * l];
       zb0 = sQNZ()[m.nz_zb + 2 * l];
@@ -313,6 +334,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();  // S2
+  PROF(1);
   // ---------------- P3: mu_b^T = W^T X^T on the tensor core
   if (tid == 0) issue_gemm(false);
   // overlapped with the MMA: AR(1) partisan non-response bias, poll_model_2020.stan:91-93 (warp 1)
@@ -353,9 +375,11 @@ __device__ __noinline__ void eval_point(const Emit em) {
       ctl.u_extra = 0.0;
     }
   }
+  PROF(2);
   // ---------------- P4: epilogue 1: TMEM -> mu_b (+prior) in the fp32 scratch
   tmem_epilogue(1.0f / 256.0f, true, 0);
   __syncthreads();  // S3
+  PROF(3);
   // ---------------- optional outputs (transformed parameters / generated quantities of this point)
   if (em.draw != nullptr) {
     float* o = em.draw;
@@ -391,7 +415,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
   if (tid < m.n_t2) t2d = __ldg(m.t2 + tid);
   // ---------------- P5: polls: linear predictor (stan:95-112), centred binomial_logit (stan:130-131), residuals
   {
-    float fsum = 0.f, gm[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, gp[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, rnat = 0.f;
+    float fsum = 0.f, rnat = 0.f, gm[MAX_MODE] = {0.f, 0.f, 0.f, 0.f}, gp[MAX_MODE] = {0.f, 0.f, 0.f, 0.f};
     const float* scr = sSCR();
     const float* qn = sQNZ();
     const float* pbrow = scr + PB_ROW * SCR_PITCH;
@@ -428,7 +452,8 @@ __device__ __noinline__ void eval_point(const Emit em) {
       if (nat) rnat += r;
       if (full) {
 #pragma unroll
-        for (int j = 0; j < MAX_MODE; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
+        for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
+        gm[MAX_MODE - 1] += r;  // total; the last class follows by difference
       }
     }
     double v0 = 0.5 * (double)qsq - (double)fsum;
@@ -443,7 +468,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
           gm[j] += __shfl_xor_sync(0xffffffffu, gm[j], off);
-          gp[j] += __shfl_xor_sync(0xffffffffu, gp[j], off);
+          if (j < MAX_MODE - 1) gp[j] += __shfl_xor_sync(0xffffffffu, gp[j], off);
         }
       }
     }
@@ -455,6 +480,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
   }
   __syncthreads();  // S4
+  PROF(4);
   // ---------------- P6: level-1 segment sums of residuals (days, pollsters, states); descriptors live in shared memory
   {
     const float* rr = sRR();
@@ -462,26 +488,50 @@ __device__ __noinline__ void eval_point(const Emit em) {
     const uint16_t* idl = SMP(uint16_t, SM_IDS);
     for (int i = tid; i < m.n_t1; i += NT) {
       const uint32_t td = t1[i];
-      const int start = td & 8191, cnt = (td >> 13) & 63, type = (td >> 19) & 3, slot = td >> 21;
+      const int start = td & 8191, cnt = (td >> 13) & 31, type = (td >> 18) & 3, slot = td >> 20;
       float acc = 0.f;
       if (type == 1) {
-        for (int j = 0; j < cnt; ++j) acc += ((sPKI()[start + j] >> 30) & 1) ? rr[start + j] : 0.f;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j)
+          if (j < cnt) acc += ((sPKI()[start + j] >> 30) & 1) ? rr[start + j] : 0.f;
       } else {
         const uint16_t* ids = idl + start;
-        for (int j = 0; j < cnt; ++j) acc += rr[ids[j]];
+        int id[SEG];
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) id[j] = (j < cnt) ? ids[j] : 0;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j)
+          if (j < cnt) acc += rr[id[j]];
       }
       sPSUM()[slot] = acc;
     }
   }
-  if (w == 0 && l < 10) {  // finalize the block reduction
+  if (w == 0 && l < 10) {  // finalize the block reduction (fixed order)
     double s = 0;
 #pragma unroll
     for (int w2 = 0; w2 < NWARP; ++w2) s += sRED()[w2 * 12 + l];
+    sRED()[NWARP * 12 + l] = s;
+    __syncwarp(0x3ffu);  // only lanes 0..9 are here
     if (l == 0) ctl.U = s + ctl.u_extra;
     else if (l == 1) ctl.rn_total = (float)s;
     else if (m.full) {
-      if (l < 2 + MAX_MODE) { if (l - 2 < m.M) sGNZ()[m.nz_m + l - 2] = m.sig_m * (float)s; }
-      else if (l - 6 < m.Pop) sGNZ()[m.nz_pop + l - 6] = m.sig_pop * (float)s;
+      // classes 0..2 are summed directly, class 3 (if present) = total - the others; total sits in slot 2+3
+      const double tot = sRED()[NWARP * 12 + 2 + (MAX_MODE - 1)];
+      if (l < 2 + MAX_MODE - 1) {
+        const int j = l - 2;
+        if (j < m.M) sGNZ()[m.nz_m + j] = m.sig_m * (float)s;
+        if (j == 0 && m.M == MAX_MODE) {
+          const double rest = tot - sRED()[NWARP * 12 + 2] - sRED()[NWARP * 12 + 3] - sRED()[NWARP * 12 + 4];
+          sGNZ()[m.nz_m + MAX_MODE - 1] = m.sig_m * (float)rest;
+        }
+      } else if (l >= 6 && l < 6 + MAX_MODE - 1) {
+        const int j = l - 6;
+        if (j < m.Pop) sGNZ()[m.nz_pop + j] = m.sig_pop * (float)s;
+        if (j == 0 && m.Pop == MAX_MODE) {
+          const double rest = tot - sRED()[NWARP * 12 + 6] - sRED()[NWARP * 12 + 7] - sRED()[NWARP * 12 + 8];
+          sGNZ()[m.nz_pop + MAX_MODE - 1] = m.sig_pop * (float)rest;
+        }
+      }
     }
   }
   // zero the operand planes (scratch reads finished at S4)
@@ -495,6 +545,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
   }
   __syncthreads();  // S5
+  PROF(5);
   // ---------------- P7: G operand cells (direct sums of residuals) and level-2 finals -> pollster gradients / g_e / g_pb row
   {
     const float* rr = sRR();
@@ -516,6 +567,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
       const uint2 td = t2d;   // prefetched before the poll phase
       const int ps = td.x & 0xffff, pc = (td.x >> 16) & 0xff, kind = td.x >> 24;
       float acc = 0.f;
+#pragma unroll 4
       for (int j = 0; j < pc; ++j) acc += ps_[ps + j];
       if (kind == 0) {
         const int t = td.y >> 6, s = td.y & 63;
@@ -524,10 +576,11 @@ __device__ __noinline__ void eval_point(const Emit em) {
         const uint32_t off = (uint32_t)(s >> 3) * A_LBO + (uint32_t)(t >> 3) * A_SBO + (uint32_t)(t & 7) * 16 + (uint32_t)(s & 7) * 2;
         *reinterpret_cast<__half*>(ahi + off) = hi;
         *reinterpret_cast<__half*>(ahi + A_PLANE + off) = lo;
-      } else if (kind == 1) {
-        sGNZ()[td.y] = m.sig_c * acc;
-      } else {
+      } else if (kind == 2) {
         sEBAR()[td.y] = acc;
+      } else {
+        const float sc = (kind == 1) ? m.sig_c : (kind == 4 ? m.sig_m : m.sig_pop);
+        sGNZ()[td.y] = sc * acc;
       }
     }
     if (tid == 0) {  // polling-bias row, national K-slot: sum of all national residuals
@@ -542,6 +595,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();  // S6
+  PROF(6);
   // ---------------- P8: H^T = G^T X  (B consumed MN-major: the same X planes, transposed view)
   if (tid == 0) issue_gemm(true);
   // overlapped: adjoint of the AR(1) recurrence (warp 1) -> gradients of raw_e_bias, mu_e_bias, rho_e_bias
@@ -584,9 +638,11 @@ __device__ __noinline__ void eval_point(const Emit em) {
       sGNZ()[m.nz_urho] = rho * (1.0f - rho) * d_rho + (1.0f - 2.0f * rho) + sQNZ()[m.nz_urho];
     }
   }
+  PROF(7);
   // ---------------- P9: epilogue 2: H -> scratch
   tmem_epilogue(m.inv_scale_G * (1.0f / 256.0f), false, 1);
   __syncthreads();  // S7
+  PROF(8);
   // ---------------- P10: forward cumulative sum of H over days; row 254 = L0^T g_pb = sum_t H[:,t]
   if (zlane) {
     float run0 = 0.f, run1 = 0.f;
@@ -604,14 +660,16 @@ __device__ __noinline__ void eval_point(const Emit em) {
     sGNZ()[m.nz_zb + tid] = m.a_b * h;
   }
   __syncthreads();  // S8
+  PROF(9);
   // ---------------- P11: gradient of U in owner layout -> TMEM
   {
     const uint32_t tp = tpriv();
     float carry0 = 0.f, carry1 = 0.f;
     if (zlane)
-      for (int w2 = 0; w2 < w; ++w2) {
+#pragma unroll
+      for (int w2 = 0; w2 < NWARP - 1; ++w2) {
         const float2 t2 = *reinterpret_cast<const float2*>(sTOT() + w2 * 52 + 2 * l);
-        carry0 += t2.x; carry1 += t2.y;
+        if (w2 < w) { carry0 += t2.x; carry1 += t2.y; }
       }
     const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
     const float* gn = sGNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
@@ -641,6 +699,7 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
     ptx::tmem_wait_st();
   }
+  PROF(10);
   // note: callers synchronise before reading ctl.U
 }
 
@@ -687,9 +746,10 @@ __device__ __forceinline__ float full_step_momentum(uint32_t tp, float hs) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float p[16], s[16], g[16];
-    tm_ld16(tp, TM_P + 16 * h, p);
-    tm_ld16(tp, TM_S + 16 * h, s);
-    tm_ld16(tp, TM_G + 16 * h, g);
+    tm_ld16_nowait(tp, TM_P + 16 * h, p);
+    tm_ld16_nowait(tp, TM_S + 16 * h, s);
+    tm_ld16_nowait(tp, TM_G + 16 * h, g);
+    ptx::tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) { p[j] = fmaf(-hs * s[j], g[j], p[j]); ss = fmaf(p[j], p[j], ss); }
     tm_st16(tp, TM_TMP + 16 * h, p);
@@ -702,9 +762,10 @@ __device__ __forceinline__ void advance(uint32_t tp, float eps_signed) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float p[16], s[16], P[16];
-    tm_ld16(tp, TM_P + 16 * h, p);
-    tm_ld16(tp, TM_S + 16 * h, s);
-    tm_ld16(tp, TM_TMP + 16 * h, P);
+    tm_ld16_nowait(tp, TM_P + 16 * h, p);
+    tm_ld16_nowait(tp, TM_S + 16 * h, s);
+    tm_ld16_nowait(tp, TM_TMP + 16 * h, P);
+    ptx::tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
       p[j] = 2.0f * P[j] - p[j];
@@ -747,13 +808,14 @@ __device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const 
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float P[16], S[16];
-    tm_ld16(tp, TM_TMP + 16 * h, P);
+    tm_ld16_nowait(tp, TM_TMP + 16 * h, P);
     if (first) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) S[j] = 0.f;
     } else {
-      tm_ld16(tp, TM_G + 16 * h, S);
+      tm_ld16_nowait(tp, TM_G + 16 * h, S);
     }
+    ptx::tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int gi = (h * 16 + j) * NT + tid;
@@ -826,9 +888,10 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float P[16], s[16], gr[16];
-      tm_ld16(tp, TM_P + 16 * h, P);
-      tm_ld16(tp, TM_S + 16 * h, s);
-      tm_ld16(tp, TM_G + 16 * h, gr);
+      tm_ld16_nowait(tp, TM_P + 16 * h, P);
+      tm_ld16_nowait(tp, TM_S + 16 * h, s);
+      tm_ld16_nowait(tp, TM_G + 16 * h, gr);
+      ptx::tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
         const float2 q0 = *qpair((h * 16 + j) >> 1);
@@ -877,9 +940,12 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
     const int nleaf = 1 << depth;
     for (int n = 0; n < nleaf; ++n) {
       const Emit none{nullptr, nullptr, nullptr};
+      PROF_DECL;
       eval_point(none);
+      PROF_RESET;
       float kk = full_step_momentum(tp, hs);
       kk = block_sum_f(kk, n & 1);
+      PROF(11);
       double h = ctl.U + 0.5 * (double)kk;
       if (!(h == h)) h = CUDART_INF;
       ++n_leap;
@@ -897,6 +963,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
           U_prop = ctl.U; H_prop = h;
         }
       }
+      PROF(12);
       // U-turn checks for every subtree this leaf completes
       const int t = __ffs(~n) - 1;  // trailing ones of n
       for (int k = 0; k < t && ok; ++k) {
@@ -910,6 +977,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         }
       }
       if (!ok) break;
+      PROF(13);
       if (n < nleaf - 1) {
         // this subtree becomes the stored left half at level t: {b, e, r}
         if (t == 0) {
@@ -922,8 +990,9 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
             float P[16], S[16], B[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) B[j] = Bsrc[(hh * 16 + j) * NT];
-            tm_ld16(tp, TM_TMP + 16 * hh, P);
-            tm_ld16(tp, TM_G + 16 * hh, S);
+            tm_ld16_nowait(tp, TM_TMP + 16 * hh, P);
+            tm_ld16_nowait(tp, TM_G + 16 * hh, S);
+            ptx::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int gi = (hh * 16 + j) * NT;
@@ -945,8 +1014,9 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float P[16], S[16];
-          tm_ld16(tp, TM_TMP + 16 * hh, P);
-          tm_ld16(tp, TM_G + 16 * hh, S);  // = old rho_top + sum of lower lefts
+          tm_ld16_nowait(tp, TM_TMP + 16 * hh, P);
+          tm_ld16_nowait(tp, TM_G + 16 * hh, S);  // = old rho_top + sum of lower lefts
+          ptx::tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int gi = (hh * 16 + j) * NT;
@@ -955,9 +1025,12 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
           }
         }
       }
+      PROF(14);
       advance(tp, eps_s);
       ptx::tc_fence_before();
       __syncthreads();
+      PROF(15);
+      if (threadIdx.x == 0) { PROF_COUNT; }
     }
     if (!ok) break;
     ++depth;
@@ -1001,8 +1074,9 @@ __device__ __noinline__ float find_stepsize(const RunArgs& a, float* ws, uint32_
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float p[16], s[16];
-      tm_ld16(tp, TM_TMP + 16 * h, p);
-      tm_ld16(tp, TM_S + 16 * h, s);
+      tm_ld16_nowait(tp, TM_TMP + 16 * h, p);
+      tm_ld16_nowait(tp, TM_S + 16 * h, s);
+      ptx::tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 16; j += 2) {
         float2* q = qpair((h * 16 + j) >> 1);
@@ -1117,6 +1191,9 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
   const int n_iter_total = a.iter_warmup + a.iter_sampling;
   const Emit none{nullptr, nullptr, nullptr};
 
+#ifdef POTUS_PROF
+  if (tid < 40) ctl.prof[tid] = 0ull;
+#endif
   for (;;) {
     __syncthreads();
     if (tid == 0) ctl.chain = atomicAdd(a.queue, 1);
@@ -1315,6 +1392,9 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
     ptx::tc_fence_before();
     __syncthreads();
   }
+#ifdef POTUS_PROF
+  if (a.prof != nullptr && tid < 40) atomicAdd(a.prof + tid, ctl.prof[tid]);
+#endif
   cta_teardown();
 }
 

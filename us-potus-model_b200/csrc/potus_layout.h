@@ -6,10 +6,12 @@
 namespace potus {
 
 // ---- CTA geometry: one chain per CTA, 16 warps.  Warp w owns days [16w,16w+16); lane l<26 owns the
-// state pair (2l,2l+1); lanes 26..31 own the non-walk ("nz") parameters.
+// state pair (2l,2l+1); lanes 26..31 own the non-walk ("nz") parameters.  (A 32-warp / 16-element variant
+// was measured 17% slower: per-phase fixed latencies -- barriers, TMEM round trips -- dominate, not occupancy.)
 constexpr int NT = 512;
 constexpr int NWARP = 16;
-constexpr int EPT = 32;                 // vector elements owned by each thread
+constexpr int DPW = 16;                 // walk days owned by each warp
+constexpr int EPT = 2 * DPW;            // vector elements owned by each thread (two tcgen05.ld/st .x16)
 constexpr int VEC = NT * EPT;           // floats per internal vector (16384, 64 KiB)
 constexpr int ZLANES = 26;              // state pairs -> S <= 52 incl. the national column
 constexpr int NZ_LANES = 6;
@@ -21,9 +23,10 @@ constexpr int ROWS = 256, KPAD = 64;
 constexpr int SCR_PITCH = 53;           // fp32 scratch pitch (odd: conflict-free row-per-lane access)
 constexpr int QZ_PITCH = 52;            // q walk block [t][52] (float2 per state pair)
 constexpr int NPOLL_CAP = 1664;
-constexpr int NT1_CAP = 1024;           // level-1 segment-sum tasks (<=32 polls each): pollster / state / day lists
+constexpr int SEG = 16;                 // polls per level-1 segment (fully unrolled, predicated)
+constexpr int NT1_CAP = 1024;           // level-1 segment-sum tasks: pollster / state / day lists
 constexpr int NCELL_CAP = 1440;         // direct (state,day) / national-day cells
-constexpr int NT2_CAP = 512;            // level-2 finals over level-1 partial sums (one per thread)
+constexpr int NT2_CAP = 1024;           // level-2 finals over level-1 partial sums (one per thread)
 constexpr int NIDS_CAP = 2 * NPOLL_CAP; // id lists (by pollster, by state)
 constexpr int MAX_MODE = 4;             // M, Pop <= 4
 constexpr int MAX_DEPTH_CAP = 10;
@@ -35,7 +38,8 @@ constexpr uint32_t A_PLANE = 8 * A_LBO; // 32896 B per hi / lo plane
 constexpr uint32_t A_REGION = 2 * A_PLANE;  // 65792 B; doubles as fp32 scratch [255][53] (54060 B)
 constexpr uint32_t B_LBO = 1024, B_SBO = 128, B_PLANE = 8192;
 
-// ---- TMEM map (512 columns): accumulators / scratch in [0,256), resident vectors in [256,512)
+// ---- TMEM map (512 columns): accumulators / scratch in [0,256), resident vectors in [256,512).
+// A thread-private vector is 32 columns per thread: thread (w,l) -> lane 32*(w%4)+l, columns 32*(w/4)..+31.
 constexpr uint32_t TM_D1 = 0, TM_D2 = 128;      // GEMM accumulators (main, cross terms)
 constexpr uint32_t TM_TMP = 0;                  // thread-private: full-step momentum P (outside GEMM phases)
 constexpr uint32_t TM_G = 128;                  // thread-private: gradient of U / merge running sum
@@ -55,11 +59,11 @@ constexpr uint32_t SM_T1 = SM_PSUM + NT1_CAP * 4;           // uint32 [NT1_CAP] 
 constexpr uint32_t SM_CELL = SM_T1 + NT1_CAP * 4;           // uint32 [NCELL_CAP] packed cells
 constexpr uint32_t SM_IDS = SM_CELL + NCELL_CAP * 4;        // uint16 [NIDS_CAP]
 constexpr uint32_t SM_E = SM_IDS + NIDS_CAP * 2;            // float e[256], ebar[256]
-constexpr uint32_t SM_TOT = SM_E + 2 * 256 * 4;             // float [16][52]
+constexpr uint32_t SM_TOT = SM_E + 2 * 256 * 4;             // float [NWARP][52]
 constexpr uint32_t SM_PRIOR = SM_TOT + NWARP * 52 * 4;      // float [64]
-constexpr uint32_t SM_RED = SM_PRIOR + 64 * 4;              // double [16][12]
-constexpr uint32_t SM_CTL = SM_RED + NWARP * 12 * 8;        // control block (scalars), 1024 B
-constexpr uint32_t SM_MODEL = SM_CTL + 1024;                // ModelDev copy, 512 B
+constexpr uint32_t SM_RED = SM_PRIOR + 64 * 4;              // double [NWARP][12]
+constexpr uint32_t SM_CTL = SM_RED + (NWARP * 12 + 16) * 8; // control block (scalars), 2048 B
+constexpr uint32_t SM_MODEL = SM_CTL + 2048;                // ModelDev copy, 512 B
 constexpr uint32_t SM_TOTAL = SM_MODEL + 512;
 static_assert(SM_TOTAL + 128 <= 232448, "shared memory budget (227 KiB) exceeded");
 static_assert(255 * SCR_PITCH * 4 <= A_REGION, "scratch must fit in the operand region");
@@ -78,12 +82,12 @@ __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o,
   return (uint32_t)s | ((uint32_t)d << 6) | ((uint32_t)p << 14) | ((uint32_t)m << 24) | ((uint32_t)o << 27) |
          ((uint32_t)un << 30);
 }
-// level-1 task (one packed word, in shared memory): start[0:13) cnt[13:19) type[19:21) psum-slot[21:31)
+// level-1 task (one packed word, in shared memory): start[0:13) cnt[13:18) type[18:20) psum-slot[20:32)
 //   type 1 contiguous*unadjusted, 2 id list; sorted by decreasing length so that a warp's threads get similar work
 // cell (one packed word, shared memory): start[0:12) cnt[12:18) dest[18:32) with dest = t*64+s  -> G operand cell
 // level-2 final: word0 = pstart[0:16) pcnt[16:24) kind[24:32); word1 = destination index
 //   kind 0: A2[t][s] operand cell (dest = t*64+s, scaled by scale_G); kind 1: gnz[dest] (scaled by sigma_c);
-//   kind 2: ebar[dest] (g_e, unscaled); kind 3: like kind 0 but summing residuals rr[pstart..pstart+pcnt) directly (poll cells)
+//   kind 2: ebar[dest] (g_e, unscaled); kind 4 / 5: gnz[dest] scaled by sigma_m / sigma_pop (mode / population sums)
 
 struct ModelDev {
   int S, T, P, M, Pop, Nn, Ns, N, full, D, NZ, npair;
@@ -131,6 +135,7 @@ struct RunArgs {
   float* draws;          // [n_chains*keep_per_chain][draw_len]
   float* monitor;        // [n_chains][iter_sampling][S+1]
   float* sampler_params; // [n_chains][iter_warmup+iter_sampling][8]
+  unsigned long long* prof; // optional [64] phase cycle counters (POTUS_PROF builds only)
 };
 
 struct EvalArgs {      // test hook: lp/grad for n vectors

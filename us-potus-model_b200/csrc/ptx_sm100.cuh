@@ -171,6 +171,20 @@ __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16])
       : "memory");
 }
 
+
+// 8-column variants (thread-private half vectors; keep register pressure low at 1024 threads / 64 regs)
+__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- fp32 -> (hi, lo) fp16 split
 // x*scale ~= hi + lo * 2^-11, 22 significant bits.
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
