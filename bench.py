@@ -103,6 +103,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def usable_cores() -> int:
+    """Host threads this process may actually use: affinity mask capped by the cgroup CPU quota
+    (a 128-CPU box whose container is limited to N CPUs must not be reported as 128 cores)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
+
+
 def ess_summary(pkg, monitor):
     """monitor: [chains, iter_sampling, S+1] on the logit scale -> Stan ESS over all chains."""
     d = pkg.diagnostics
@@ -117,7 +136,7 @@ def run_cpu(args, data, pkg, reference_line: bool):
     import orc
     orc.build()
     om = orc.OracleModel(data)
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     iters = args.cpu_iters
 
     def one(seed):
@@ -158,7 +177,7 @@ def main():
     ap.add_argument("--iter-sampling", type=int, default=500)
     ap.add_argument("--keep-per-chain", type=int, default=3, help="full draws kept per chain (1024x3 ~ the reference's 6x500)")
     ap.add_argument("--seed", type=int, default=1843)
-    ap.add_argument("--cpu-iters", type=int, default=24, help="bounded CPU sample: iterations per chain")
+    ap.add_argument("--cpu-iters", type=int, default=10, help="bounded CPU sample: iterations per chain")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warmup-scale", type=float, default=0.1,
                     help="untimed warm-up steps run the same chains for this fraction of the iterations (clock/cache warm-up)")

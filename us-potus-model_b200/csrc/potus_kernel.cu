@@ -38,6 +38,10 @@ struct Ctl {
   alignas(16) float kred[2][NWARP];
   alignas(16) float mred[NWARP][8];
   ChainState cs;
+  // per-transition statistics kept by thread 0 (not needed for control flow)
+  double U_samp, H_samp, U_prop, H_prop;
+  float sum_metro;
+  int pad1;
 #ifdef POTUS_PROF
   unsigned long long prof[40];
 #endif
@@ -261,7 +265,7 @@ __device__ __forceinline__ void issue_gemm(bool b_mn_major) {
 // held in shared memory.  Called by all 512 threads.  Both mbarriers complete exactly twice per call,
 // so their phase parity is 0 for GEMM 1 and 1 for GEMM 2 on every call.
 // ================================================================================================
-__device__ __noinline__ void eval_point(const Emit em) {
+__device__ __forceinline__ void eval_body(const Emit em) {
   const ModelDev& m = MD();
   Ctl& ctl = CTL();
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -273,7 +277,8 @@ __device__ __noinline__ void eval_point(const Emit em) {
   PROF_DECL;
 
   // ---------------- P1: reverse scan of the walk innovations (poll_model_2020.stan:86 collapsed)
-  float c[32];
+  // (the running sums are recomputed from shared memory in P2 / P11 instead of being carried in 32 registers
+  //  across the barriers: this kernel runs at the 128-register limit)
   if (zlane) {
     float run0 = 0.f, run1 = 0.f;
     const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
@@ -282,7 +287,6 @@ __device__ __noinline__ void eval_point(const Emit em) {
       const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
       qsq = fmaf(z.x, z.x, fmaf(z.y, z.y, qsq));
       if (d < ndw) { run0 += z.x; run1 += z.y; }
-      c[2 * d] = run0; c[2 * d + 1] = run1;
     }
     *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
   } else {
@@ -315,11 +319,14 @@ __device__ __noinline__ void eval_point(const Emit em) {
     }
     const float base0 = m.a_T * zt0 + m.a_w * carry0, base1 = m.a_T * zt1 + m.a_w * carry1;
     unsigned char* ap = smem_raw + SM_A + (uint32_t)(l >> 2) * A_LBO + (uint32_t)(l & 3) * 4 + (uint32_t)(2 * w) * A_SBO;
+    const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
+    float run0 = 0.f, run1 = 0.f;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
+    for (int d = 15; d >= 0; --d) {
       float v0 = 0.f, v1 = 0.f;
+      if (d < ndw) { const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH); run0 += z.x; run1 += z.y; }
       if (act) {
-        if (d < nd) { v0 = fmaf(m.a_w, c[2 * d], base0); v1 = fmaf(m.a_w, c[2 * d + 1], base1); }
+        if (d < nd) { v0 = fmaf(m.a_w, run0, base0); v1 = fmaf(m.a_w, run1, base1); }
         else if (16 * w + d == PB_ROW) { v0 = m.a_b * zb0; v1 = m.a_b * zb1; }
         if (2 * l + 1 >= S) v1 = 0.f;
       }
@@ -648,10 +655,8 @@ __device__ __noinline__ void eval_point(const Emit em) {
     float run0 = 0.f, run1 = 0.f;
     const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
 #pragma unroll
-    for (int d = 0; d < 16; ++d) {
+    for (int d = 0; d < 16; ++d)
       if (d < nd) { run0 += hz[d * SCR_PITCH]; run1 += hz[d * SCR_PITCH + 1]; }
-      c[2 * d] = run0; c[2 * d + 1] = run1;
-    }
     *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
   }
   if (tid < S) {  // gradient sources of raw_mu_b_T and raw_polling_bias share the spare GEMM row
@@ -674,6 +679,8 @@ __device__ __noinline__ void eval_point(const Emit em) {
     const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
     const float* gn = sGNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
     const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
+    const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
+    float pre0 = carry0, pre1 = carry1;   // running prefix of H over days (this warp's rows)
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float g[16];
@@ -682,9 +689,10 @@ __device__ __noinline__ void eval_point(const Emit em) {
         for (int j = 0; j < 16; j += 2) {
           const int d = (h * 16 + j) >> 1;
           const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
+          if (d < nd) { pre0 += hz[d * SCR_PITCH]; pre1 += hz[d * SCR_PITCH + 1]; }
           const bool walk = d < ndw;
-          g[j] = walk ? fmaf(-m.a_w, c[2 * d] + carry0, z.x) : z.x;
-          g[j + 1] = walk ? fmaf(-m.a_w, c[2 * d + 1] + carry1, z.y) : z.y;
+          g[j] = walk ? fmaf(-m.a_w, pre0, z.x) : z.x;
+          g[j + 1] = walk ? fmaf(-m.a_w, pre1, z.y) : z.y;
         }
       } else {
 #pragma unroll
@@ -702,6 +710,10 @@ __device__ __noinline__ void eval_point(const Emit em) {
   PROF(10);
   // note: callers synchronise before reading ctl.U
 }
+
+// out-of-line copy for the cold call sites (initial point of a transition, step-size search, inits, final draw);
+// the leaf loop of transition() inlines eval_body so that registers are allocated across the whole loop body
+__device__ __noinline__ void eval_point(const Emit em) { eval_body(em); }
 
 // ================================================================================================
 // small block-wide helpers
@@ -913,8 +925,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
     }
   }
   int samp = SLOT_CAND_A, prop = SLOT_CAND_B;
-  double U_samp = U0, H_samp = H0, U_prop = U0, H_prop = H0;
-  float lsw = 0.f, sum_metro = 0.f;
+  if (tid == 0) { ctl.U_samp = U0; ctl.H_samp = H0; ctl.U_prop = U0; ctl.H_prop = H0; ctl.sum_metro = 0.f; }
+  float lsw = 0.f;
   int n_leap = 0, depth = 0, loaded = 0;
   bool divergent = false;
 
@@ -941,7 +953,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
     for (int n = 0; n < nleaf; ++n) {
       const Emit none{nullptr, nullptr, nullptr};
       PROF_DECL;
-      eval_point(none);
+      eval_body(none);
       PROF_RESET;
       float kk = full_step_momentum(tp, hs);
       kk = block_sum_f(kk, n & 1);
@@ -952,7 +964,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       const float dH = (float)(H0 - h);  // energy differences are O(1): fp32 is ample for the weights
       if (h - H0 > 1000.0) divergent = true;
       lsw_sub = logaddexp_f(lsw_sub, dH);
-      sum_metro += (dH > 0.f) ? 1.0f : __expf(dH);
+      if (tid == 0) ctl.sum_metro += (dH > 0.f) ? 1.0f : __expf(dH);
       if (divergent) { ok = false; break; }
       // multinomial selection inside the new subtree (reservoir form of Stan's pairwise rule)
       {
@@ -960,43 +972,45 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         rng_words(a.seed, chain_gid, (uint32_t)n_leap, iter, 3, 0, sw);
         if (n == 0 || u01(sw[0]) < __expf(dH - lsw_sub)) {
           q_to_global(slot_ptr(ws, prop));
-          U_prop = ctl.U; H_prop = h;
+          if (tid == 0) { ctl.U_prop = ctl.U; ctl.H_prop = h; }
         }
       }
       PROF(12);
       // U-turn checks for every subtree this leaf completes
       const int t = __ffs(~n) - 1;  // trailing ones of n
+      // FIRST[z] holds the momentum of the first leaf of every live subtree: leaf m goes to slot z = tz(m)
+      // (m = 0: z = depth).  It is not overwritten before leaf m + 2^(z+1), i.e. after every subtree that
+      // starts at m has been merged -- so left summaries need no copy of their first momentum.
+      auto first_slot = [&](int mleaf) -> float* {
+        const int z = mleaf ? (__ffs(mleaf) - 1) : depth;
+        return slot_ptr(ws, SLOT_LEFT + 3 * (z - 1));
+      };
       for (int k = 0; k < t && ok; ++k) {
         if (k == 0) {
-          const float* L0p = slot_ptr(ws, SLOT_LEFT0);
+          const float* L0p = first_slot(n - 1);   // the previous (even) leaf
           ok = merge_check(tp, L0p, L0p, L0p, nullptr, true, true);
         } else {
           const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
-          const float* Rb = (k == 1) ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (k - 2));
-          ok = merge_check(tp, Lk, Lk + VEC, Lk + 2 * VEC, Rb, false, false);
+          ok = merge_check(tp, first_slot(n - (2 << k) + 1), Lk + VEC, Lk + 2 * VEC, first_slot(n - (1 << k) + 1), false, false);
         }
       }
       if (!ok) break;
       PROF(13);
       if (n < nleaf - 1) {
-        // this subtree becomes the stored left half at level t: {b, e, r}
         if (t == 0) {
-          tm_to_global(tp, TM_TMP, slot_ptr(ws, SLOT_LEFT0));
+          tm_to_global(tp, TM_TMP, first_slot(n));   // an even leaf starts subtrees at levels 0..tz(n)
         } else {
+          // this subtree becomes the stored left half at level t: {e, r} (its b is FIRST[...])
           float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1)) + tid;
-          const float* Bsrc = ((t == 1) ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (t - 2))) + tid;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            float P[16], S[16], B[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) B[j] = Bsrc[(hh * 16 + j) * NT];
+            float P[16], S[16];
             tm_ld16_nowait(tp, TM_TMP + 16 * hh, P);
             tm_ld16_nowait(tp, TM_G + 16 * hh, S);
             ptx::tmem_wait_ld();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int gi = (hh * 16 + j) * NT;
-              Lt[gi] = B[j];
               Lt[VEC + gi] = P[j];
               Lt[2 * VEC + gi] = P[j] + S[j];
             }
@@ -1007,7 +1021,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         // base_nuts::transition) and fold it into the tree summary
         const float* F = slot_ptr(ws, dir > 0 ? SLOT_TOP_BB : SLOT_TOP_FF);
         const float* A = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB);
-        const float* Rb = (depth == 0) ? nullptr : (depth == 1 ? slot_ptr(ws, SLOT_LEFT0) : slot_ptr(ws, SLOT_LEFT + 3 * (depth - 2)));
+        const float* Rb = (depth == 0) ? nullptr : first_slot(0);
         persist = merge_check(tp, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0, false);
         float* rho = slot_ptr(ws, SLOT_TOP_RHO) + tid;
         float* endv = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB) + tid;
@@ -1037,7 +1051,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
     // biased progressive sampling at the top level
     if (lsw_sub > lsw || u01(rw[1]) < __expf(lsw_sub - lsw)) {
       const int tmp = samp; samp = prop; prop = tmp;
-      U_samp = U_prop; H_samp = H_prop;
+      if (tid == 0) { ctl.U_samp = ctl.U_prop; ctl.H_samp = ctl.H_prop; }
     }
     lsw = logaddexp_f(lsw, lsw_sub);
     if (!persist) break;
@@ -1045,11 +1059,12 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
   global_to_q(slot_ptr(ws, samp));
   ptx::tc_fence_before();
   __syncthreads();
-  st.lp = (float)(-U_samp);  // centred; the host adds lp_const in fp64 (fp32 cannot hold -1.2e6 to 1e-2)
-  st.accept = sum_metro / (float)(n_leap > 0 ? n_leap : 1);
+  // (thread 0 wrote the statistics before the barrier above; every thread returns the same values)
+  st.lp = (float)(-ctl.U_samp);  // centred; the host adds lp_const in fp64 (fp32 cannot hold -1.2e6 to 1e-2)
+  st.accept = ctl.sum_metro / (float)(n_leap > 0 ? n_leap : 1);
   st.eps = eps; st.depth = (float)depth; st.nleap = (float)n_leap; st.divergent = divergent ? 1.f : 0.f;
-  st.energy = (float)H_samp;
-  if (tid == 0) { ctl.cs.n_leapfrog += n_leap; ctl.cs.U = (float)U_samp; }
+  st.energy = (float)ctl.H_samp;
+  if (tid == 0) { ctl.cs.n_leapfrog += n_leap; ctl.cs.U = (float)ctl.U_samp; }
 }
 
 // Stan base_hmc::init_stepsize: double / halve eps until the one-step acceptance crosses 0.8

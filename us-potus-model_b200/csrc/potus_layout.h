@@ -69,8 +69,9 @@ static_assert(SM_TOTAL + 128 <= 232448, "shared memory budget (227 KiB) exceeded
 static_assert(255 * SCR_PITCH * 4 <= A_REGION, "scratch must fit in the operand region");
 
 // ---- workspace slots (per CTA, VEC floats each)
-constexpr int SLOT_LEFT0 = 0;                    // Left_0 {b=e=r}
-constexpr int SLOT_LEFT = 1;                     // Left_k {b,e,r} at 1 + 3*(k-1) + {0,1,2}, k = 1..9
+constexpr int SLOT_LEFT0 = 0;                    // (unused)
+constexpr int SLOT_LEFT = 1;                     // level k = 1..9 at 1 + 3*(k-1): +0 FIRST[k] (first-leaf momentum, see transition()),
+                                                 // +1 Left_k.e, +2 Left_k.r
 constexpr int SLOT_TOP_BB = 28, SLOT_TOP_FF = 29, SLOT_TOP_RHO = 30;
 constexpr int SLOT_ENDF_Q = 31, SLOT_ENDF_P = 32, SLOT_ENDB_Q = 33, SLOT_ENDB_P = 34;
 constexpr int SLOT_CAND_A = 35, SLOT_CAND_B = 36; // sample / proposal positions (roles swap)
