@@ -1041,8 +1041,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       }
       PROF(14);
       advance(tp, eps_s);
-      ptx::tc_fence_before();
-      __syncthreads();
+      // no barrier here: the next phase (P1 of the next leaf, or the end-of-subtree bookkeeping) only touches the
+      // calling thread's own position elements; the first cross-thread read of q comes after barrier S1
       PROF(15);
       if (threadIdx.x == 0) { PROF_COUNT; }
     }
