@@ -145,3 +145,23 @@ def test_posterior_matches_reference_tables_2008_no_mode(pkg, datalists, cuda_li
     dh = max(abs(hi[i] - tab[s]["high"]) for i, s in enumerate(names))
     print(f"2008 vs README: max|dmean| {dm:.4f} |dlow| {dl:.4f} |dhigh| {dh:.4f}")
     assert dm <= 0.003 and dl <= 0.012 and dh <= 0.012
+
+
+def test_posterior_matches_reference_tables_2012_no_mode(pkg, datalists, cuda_lib):
+    """The 2012 backtest (no-mode model, final_2012.R) vs README.md:179-232, and vs the long fp64 oracle run."""
+    d = datalists[2012]
+    fit = pkg.cmdstan_model("poll_model_2020_no_mode_adjustment.stan").sample(data=d, seed=1843, chains=148, iter_warmup=500,
+                                                                              iter_sampling=200, keep_per_chain=1)
+    p = 1 / (1 + np.exp(-fit.monitor().reshape(-1, 52)))
+    p[:, 51] = p[:, :51] @ d["state_weights"]
+    names = [str(s) for s in d["_state_names"]] + ["\u2013"]
+    tab = {r["state"]: r for r in json.load(open(os.path.join(GOLDEN, "readme_tables.json")))["2012"]}
+    mean, lo, hi = p.mean(0), np.quantile(p, 0.025, axis=0), np.quantile(p, 0.975, axis=0)
+    dm = max(abs(mean[i] - tab[s]["mean"]) for i, s in enumerate(names))
+    dl = max(abs(lo[i] - tab[s]["low"]) for i, s in enumerate(names))
+    dh = max(abs(hi[i] - tab[s]["high"]) for i, s in enumerate(names))
+    print(f"2012 vs README: max|dmean| {dm:.4f} |dlow| {dl:.4f} |dhigh| {dh:.4f}")
+    assert dm <= 0.003 and dl <= 0.012 and dh <= 0.012
+    ora = json.load(open(os.path.join(GOLDEN, "oracle_posterior_2012.json")))
+    z = np.abs(mean - np.array(ora["mean"])) / (4 * np.array(ora["mcse"]) + 5e-4)
+    assert z.max() <= 1.0, z.max()
