@@ -128,6 +128,13 @@ def test_posterior_matches_reference_tables_2016(pkg, datalists, cuda_lib):
     assert z.max() <= 1.0, z.max()
     ess = pkg.diagnostics.ess(p[:, 9].reshape(296, 200))
     assert ess > 0.2 * p.shape[0]
+    # the reports' headline numbers (README.md:260): Brier scores and states called, from OUR draws
+    sh = pkg.postprocess.election_day_shares(fit.monitor())
+    tab_ = pkg.postprocess.state_table(sh, d["_state_names"])
+    b = pkg.postprocess.brier_scores(tab_["prob"], d["_state_names"], d["_ev_state"], 2016)
+    pub = pkg.postprocess.PUBLISHED_BRIER[2016]
+    print("2016 Brier", b, "published", pub)
+    assert abs(b["ev_wtd_brier"] - pub[0]) < 0.006 and abs(b["unwtd_brier"] - pub[1]) < 0.004 and abs(b["states_correct"] - pub[2]) <= 1
 
 
 def test_posterior_matches_reference_tables_2008_no_mode(pkg, datalists, cuda_lib):

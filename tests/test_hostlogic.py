@@ -98,3 +98,22 @@ def test_allgather_ordering_gloo_world2():
     for r in (0, 1):
         a = got[r].reshape(6, 2, 5)
         assert np.array_equal(a[:, 0, 0], np.arange(6) * 1000.0) and np.array_equal(a[:, 1, 0], np.arange(6) * 1000.0 + 1)
+
+
+def test_brier_restatement_reproduces_published_scores(pkg, datalists):
+    """Feeding the reference's own published P(win) column (README tables, 3 d.p.) through the restated Brier
+    computation (README.Rmd:378-390) gives the published scores (README.md:75,169,260) to the rounding of the inputs."""
+    import json
+    from conftest import GOLDEN
+    tabs = json.load(open(os.path.join(GOLDEN, "readme_tables.json")))
+    for year, d in datalists.items():
+        rows = {r["state"]: r for r in tabs[str(year)]}
+        states = [str(s) for s in d["_state_names"]]
+        prob = np.array([rows[s]["prob"] for s in states])
+        b = pkg.postprocess.brier_scores(prob, states, d["_ev_state"], year)
+        pub = pkg.postprocess.PUBLISHED_BRIER[year]
+        assert abs(b["ev_wtd_brier"] - pub[0]) < 4e-4 and abs(b["unwtd_brier"] - pub[1]) < 4e-4, (year, b, pub)
+        assert b["states_correct"] == pub[2]
+    sh = np.random.default_rng(0).uniform(0.3, 0.7, (100, 51))
+    ec = pkg.postprocess.electoral_college(sh, datalists[2016]["_ev_state"])
+    assert 0 <= ec["prob"] <= 1 and datalists[2016]["_ev_state"].sum() == 538

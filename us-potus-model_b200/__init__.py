@@ -9,9 +9,11 @@ Holds only what the hot path needs:
   datalist.py  the named data list of final_20{08,12,16}.R (the reference's host language, R, is
                not in this image)
   diagnostics.py  Stan-style ESS / R-hat for the benchmark metric
+  postprocess.py  the reports' election-day summaries (state table, national vote, EV simulation, Brier)
   build.py     nvcc recipe
 """
 from . import datalist  # noqa: F401
 from .datalist import build_datalist, synthetic_datalist, load_npz, save_npz  # noqa: F401
 from .model import cmdstan_model, PotusFit, logp_grad  # noqa: F401
 from . import diagnostics  # noqa: F401
+from . import postprocess  # noqa: F401
