@@ -128,11 +128,11 @@ int check_supported(const PotusData* d) {
   char buf[256];
   const bool full = d->poll_mode_state != nullptr;
   const int N = d->N_state_polls + d->N_national_polls;
-  if (d->S > MAX_S || d->T > MAX_T || N > NPOLL_CAP || d->P > 1023 || (full && (d->M > MAX_MODE || d->Pop > MAX_MODE))) {
+  if (d->S > MAX_S || d->T > MAX_T || N > NPOLL_CAP - SEG || d->P > 1023 || (full && (d->M > MAX_MODE || d->Pop > MAX_MODE))) {
     snprintf(buf, sizeof buf,
              "problem size S=%d T=%d N=%d P=%d M=%d Pop=%d is outside the resident kernel's limits (S<=%d, T<=%d, N<=%d, P<=1023, M,Pop<=%d); "
              "the streaming large-S/T variant (BASELINE config 5) is not built yet",
-             d->S, d->T, N, d->P, d->M, d->Pop, MAX_S, MAX_T, NPOLL_CAP, MAX_MODE);
+             d->S, d->T, N, d->P, d->M, d->Pop, MAX_S, MAX_T, NPOLL_CAP - SEG, MAX_MODE);
     return fail(POTUS_ERR_UNSUPPORTED, buf);
   }
   if (full)
@@ -339,7 +339,7 @@ int build_model(const PotusData* d, HostModel& hm) {
   // balance: longest tasks first, so thread i of every warp gets tasks of similar length
   std::stable_sort(t1.begin(), t1.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
   std::stable_sort(t2.begin(), t2.end(), [](const uint2& a, const uint2& b) { return ((a.x >> 16) & 0xff) > ((b.x >> 16) & 0xff); });
-  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || (int)t2.size() > NT || (int)ids.size() > NIDS_CAP || (int)cells.size() > NCELL_CAP)
+  if ((int)t1.size() > NT1_CAP || (int)t2.size() > NT2_CAP || (int)t2.size() > NT || (int)ids.size() + SEG > NIDS_CAP || (int)cells.size() > NCELL_CAP)
     return fail(POTUS_ERR_UNSUPPORTED, "poll structure needs more segment tasks than the resident kernel holds");
   std::stable_sort(cells.begin(), cells.end(), [](uint32_t a, uint32_t b) { return ((a >> 12) & 63) > ((b >> 12) & 63); });
   std::vector<uint32_t> t1p(NT1_CAP, 0u);
@@ -578,7 +578,7 @@ int potus_run(PotusSampler* s) {
     unsigned long long hp[64];
     if (cudaMemcpy(hp, s->prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess) {
       fprintf(stderr, "[potus_prof] leaves=%llu cycles/leaf per phase (thread 0, summed over CTAs):", hp[39]);
-      for (int i = 0; i < 16; ++i) fprintf(stderr, " p%d=%.0f", i, hp[39] ? (double)hp[i] / (double)hp[39] : 0.0);
+      for (int i = 0; i < 24; ++i) fprintf(stderr, " p%d=%.0f", i, hp[39] ? (double)hp[i] / (double)hp[39] : 0.0);
       fprintf(stderr, "\n");
     }
   }

@@ -463,6 +463,7 @@ __device__ __forceinline__ void eval_body(const Emit em) {
         gm[MAX_MODE - 1] += r;  // total; the last class follows by difference
       }
     }
+    PROF(16);
     double v0 = 0.5 * (double)qsq - (double)fsum;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -486,6 +487,7 @@ __device__ __forceinline__ void eval_body(const Emit em) {
       for (int j = 0; j < MAX_MODE; ++j) { red[2 + j] = (double)gm[j]; red[6 + j] = (double)gp[j]; }
     }
   }
+  PROF(17);
   __syncthreads();  // S4
   PROF(4);
   // ---------------- P6: level-1 segment sums of residuals (days, pollsters, states); descriptors live in shared memory
@@ -496,51 +498,45 @@ __device__ __forceinline__ void eval_body(const Emit em) {
     for (int i = tid; i < m.n_t1; i += NT) {
       const uint32_t td = t1[i];
       const int start = td & 8191, cnt = (td >> 13) & 31, type = (td >> 18) & 3, slot = td >> 20;
+      // loads are unconditional (arrays are padded so that reading SEG entries is always in bounds) and only the
+      // accumulation is predicated: all SEG loads issue back to back instead of SEG serialized latencies.  Neighbouring
+      // threads hold neighbouring segments of one list (starts differ by SEG = 16 words): each lane walks its segment
+      // rotated by its lane id so a warp's 32 accesses fall into 32 different banks instead of 2.  NOTE: the summation
+      // order inside a segment therefore depends on the lane, but is fixed for a given task -> still deterministic.
       float acc = 0.f;
       if (type == 1) {
+        float v[SEG];
+        uint32_t ixs[SEG];
 #pragma unroll
-        for (int j = 0; j < SEG; ++j)
-          if (j < cnt) acc += ((sPKI()[start + j] >> 30) & 1) ? rr[start + j] : 0.f;
+        for (int j = 0; j < SEG; ++j) { const int jj = (j + l) & (SEG - 1); v[j] = rr[start + jj]; ixs[j] = sPKI()[start + jj]; }
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) acc += ((((j + l) & (SEG - 1)) < cnt) && ((ixs[j] >> 30) & 1)) ? v[j] : 0.f;
       } else {
         const uint16_t* ids = idl + start;
         int id[SEG];
 #pragma unroll
-        for (int j = 0; j < SEG; ++j) id[j] = (j < cnt) ? ids[j] : 0;
+        for (int j = 0; j < SEG; ++j) id[j] = ids[(j + l) & (SEG - 1)];
+        float v[SEG];
 #pragma unroll
-        for (int j = 0; j < SEG; ++j)
-          if (j < cnt) acc += rr[id[j]];
+        for (int j = 0; j < SEG; ++j) v[j] = rr[id[j]];
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) acc += (((j + l) & (SEG - 1)) < cnt) ? v[j] : 0.f;
       }
       sPSUM()[slot] = acc;
     }
   }
-  if (w == 0 && l < 10) {  // finalize the block reduction (fixed order)
-    double s = 0;
+  PROF(18);
+  if (w < 10) {  // finalize the block reduction: warp v reduces value v (fixed shuffle tree => deterministic)
+    double sv = (l < NWARP) ? sRED()[l * 12 + w] : 0.0;
 #pragma unroll
-    for (int w2 = 0; w2 < NWARP; ++w2) s += sRED()[w2 * 12 + l];
-    sRED()[NWARP * 12 + l] = s;
-    __syncwarp(0x3ffu);  // only lanes 0..9 are here
-    if (l == 0) ctl.U = s + ctl.u_extra;
-    else if (l == 1) ctl.rn_total = (float)s;
-    else if (m.full) {
-      // classes 0..2 are summed directly, class 3 (if present) = total - the others; total sits in slot 2+3
-      const double tot = sRED()[NWARP * 12 + 2 + (MAX_MODE - 1)];
-      if (l < 2 + MAX_MODE - 1) {
-        const int j = l - 2;
-        if (j < m.M) sGNZ()[m.nz_m + j] = m.sig_m * (float)s;
-        if (j == 0 && m.M == MAX_MODE) {
-          const double rest = tot - sRED()[NWARP * 12 + 2] - sRED()[NWARP * 12 + 3] - sRED()[NWARP * 12 + 4];
-          sGNZ()[m.nz_m + MAX_MODE - 1] = m.sig_m * (float)rest;
-        }
-      } else if (l >= 6 && l < 6 + MAX_MODE - 1) {
-        const int j = l - 6;
-        if (j < m.Pop) sGNZ()[m.nz_pop + j] = m.sig_pop * (float)s;
-        if (j == 0 && m.Pop == MAX_MODE) {
-          const double rest = tot - sRED()[NWARP * 12 + 6] - sRED()[NWARP * 12 + 7] - sRED()[NWARP * 12 + 8];
-          sGNZ()[m.nz_pop + MAX_MODE - 1] = m.sig_pop * (float)rest;
-        }
-      }
+    for (int off = 8; off > 0; off >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, off);
+    if (l == 0) {
+      if (w == 0) ctl.U = sv + ctl.u_extra;
+      else if (w == 1) ctl.rn_total = (float)sv;
+      else sRED()[NWARP * 12 + w] = sv;   // mode / population class sums, combined after barrier S5
     }
   }
+  PROF(19);
   // zero the operand planes (scratch reads finished at S4)
   {
     uint4* a4 = SMP(uint4, SM_A);
@@ -551,6 +547,7 @@ __device__ __forceinline__ void eval_body(const Emit em) {
       if (k < (int)(A_REGION / 16)) a4[k] = z;
     }
   }
+  PROF(20);
   __syncthreads();  // S5
   PROF(5);
   // ---------------- P7: G operand cells (direct sums of residuals) and level-2 finals -> pollster gradients / g_e / g_pb row
@@ -588,6 +585,18 @@ __device__ __forceinline__ void eval_body(const Emit em) {
       } else {
         const float sc = (kind == 1) ? m.sig_c : (kind == 4 ? m.sig_m : m.sig_pop);
         sGNZ()[td.y] = sc * acc;
+      }
+    }
+    if (m.full && tid >= 32 && tid < 32 + 2 * MAX_MODE) {  // mode / population gradients from the class sums
+      const int j = (tid - 32) % MAX_MODE;
+      const bool ispop = (tid - 32) >= MAX_MODE;
+      const int ncls = ispop ? m.Pop : m.M;
+      const double* cls = sRED() + NWARP * 12 + (ispop ? 6 : 2);
+      const double tot = sRED()[NWARP * 12 + 2 + (MAX_MODE - 1)];   // sum over all polls
+      if (j < ncls) {
+        double v = cls[j];
+        if (j == MAX_MODE - 1) v = tot - sRED()[NWARP * 12 + (ispop ? 6 : 2)] - sRED()[NWARP * 12 + (ispop ? 7 : 3)] - sRED()[NWARP * 12 + (ispop ? 8 : 4)];
+        sGNZ()[(ispop ? m.nz_pop : m.nz_m) + j] = (ispop ? m.sig_pop : m.sig_m) * (float)v;
       }
     }
     if (tid == 0) {  // polling-bias row, national K-slot: sum of all national residuals
