@@ -88,3 +88,21 @@ def test_chain_rng_is_keyed_by_global_chain_id(small):
     a = om.sample(chains=2, iter_warmup=20, iter_sampling=5, threads=2, tree_mode=1)
     b = om.sample(chains=1, iter_warmup=20, iter_sampling=5, threads=1, tree_mode=1, chain_id_offset=1)
     assert np.array_equal(a["monitor"][1], b["monitor"][0])
+
+
+def test_config0_2008_backtest_plumbing(orc_mod, datalists):
+    """BASELINE.json configs[0]: the repo's own 2008 backtest at 2 chains x 200 iterations (100 warm-up => Stan's
+    15/75/10 % window rule), run through the CPU oracle because rstan is not installable here.  Plumbing check:
+    data list -> sampler -> election-day table lands on the published one (README.md:83-136) within the Monte-Carlo
+    error of 200 draws."""
+    import json, os
+    from conftest import GOLDEN
+    d = datalists[2008]
+    om = orc_mod.OracleModel(d)
+    r = om.sample(chains=2, iter_warmup=100, iter_sampling=100, seed=1843, threads=2, literal=True, tree_mode=0)
+    assert r["stats"][:, 100:, 5].sum() == 0
+    p = 1 / (1 + np.exp(-r["monitor"].reshape(-1, 52)))[:, :51]
+    tab = {row["state"]: row for row in json.load(open(os.path.join(GOLDEN, "readme_tables.json")))["2008"]}
+    names = [str(s) for s in d["_state_names"]]
+    dm = max(abs(p[:, i].mean() - tab[s]["mean"]) for i, s in enumerate(names))
+    assert dm < 0.012, dm
