@@ -115,7 +115,9 @@ POTUS_API size_t potus_draws_size(const PotusSampler* s, const char* par);
  *   "theta" [draws,D] (unconstrained, Stan order)
  *   "monitor" [iter_sampling*chains, S+1]  every sampling iteration: mu_b[,T] and national_mu_b_average[T]
  *   "sampler_params" [(iter_warmup+iter_sampling)*chains, 7]
- *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__          */
+ *        lp__, accept_stat__, stepsize__, treedepth__, n_leapfrog__, divergent__, energy__
+ *   "inv_metric" [chains, D]  adapted diagonal of the inverse metric per chain (the numbers CmdStan prints
+ *        under "# Diagonal elements of inverse mass matrix:"), Stan unconstrained order               */
 POTUS_API int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
 POTUS_API int potus_get_stats(PotusSampler* s, PotusStats* stats);
 /* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py):

@@ -76,6 +76,23 @@ def test_output_contract(pkg, orc_mod, datalists, cuda_lib):
     assert fit.model_name == "poll_model_2020"
     with pytest.raises(KeyError):
         fit.extract("mu_a")
+    # f3: CmdStan CSV files (what rstan::read_stan_csv parses, final_2016.R:543) hold the same draws
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        paths = fit.save_csvfiles(td, chains=[0, 3])
+        back = pkg.stancsv.read_stan_csv(paths)
+    assert back["names"] == pkg.stancsv.column_names(d) and len(back["names"]) == 43360
+    for j, c in enumerate((0, 3)):
+        for k in range(4):
+            r = c * 4 + k
+            assert np.abs(back["draws"]["mu_b"][k, j] - ex["mu_b"][r]).max() < 2e-6
+            assert np.abs(back["draws"]["predicted_score"][k, j] - ex["predicted_score"][r]).max() < 2e-6
+            assert np.abs(back["draws"]["raw_mu_b_T"][k, j] - th[r, :51]).max() < 1e-5
+            assert abs(back["sampler_params"]["lp__"][k, j] - sp["lp__"][c, 30 + 2 * k + 1]) < 6.0   # 6 significant figures of -1.17e6
+    im = fit.inv_metric()
+    assert im.shape == (4, 15098) and (im > 0).all() and np.isfinite(im).all()
+    assert np.allclose(back["inv_metric"][1], im[3], rtol=1e-4)
+    assert abs(back["stepsize"][0] - sp["stepsize__"][0, -1]) < 1e-6
 
 
 def test_no_mode_variant_runs_and_hides_full_only_pars(pkg, datalists, cuda_lib):

@@ -117,3 +117,100 @@ def test_brier_restatement_reproduces_published_scores(pkg, datalists):
     sh = np.random.default_rng(0).uniform(0.3, 0.7, (100, 51))
     ec = pkg.postprocess.electoral_college(sh, datalists[2016]["_ev_state"])
     assert 0 <= ec["prob"] <= 1 and datalists[2016]["_ev_state"].sum() == 538
+
+
+class _StubFit:
+    """Quacks like PotusFit with draws taken from the fp64 oracle (no GPU here): exercises the CSV layer."""
+
+    def __init__(self, data, theta, chains, keep, iter_warmup, iter_sampling):
+        from types import SimpleNamespace
+        from oracle import potus_oracle as po
+        self.data, self._theta = data, theta
+        self.cfg = SimpleNamespace(chains=chains, iter_warmup=iter_warmup, iter_sampling=iter_sampling, seed=1843,
+                                   adapt_delta=0.8, max_treedepth=10, init_radius=2.0, chain_id_offset=0)
+        self.model_name = "poll_model_2020" if "poll_mode_state" in data else "poll_model_2020_no_mode_adjustment"
+        self.stats = dict(seconds_warmup=1.5, seconds_sampling=2.5)
+        self.n_draws = chains * keep
+        self._cd = [po.constrained_draw(t, data) for t in theta]
+        self._fw = [po.forward_closed(t, data) for t in theta]
+        rng = np.random.default_rng(5)
+        n_it = iter_warmup + iter_sampling
+        self._sp = {k: rng.random((chains, n_it)) for k in
+                    ("lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__")}
+        self._im = rng.random((chains, theta.shape[1])) + 0.1
+
+    def theta(self):
+        return self._theta
+
+    def extract(self, pars):
+        return {p: np.stack([c[p] for c in self._cd]) for p in pars}
+
+    def sampler_params(self, inc_warmup=True):
+        return self._sp if inc_warmup else {k: v[:, self.cfg.iter_warmup:] for k, v in self._sp.items()}
+
+    def inv_metric(self):
+        return self._im
+
+
+@pytest.mark.parametrize("year", [2016, 2008])
+def test_stan_csv_layout_and_roundtrip(pkg, datalists, year, tmp_path):
+    """f3: CmdStan CSV columns in Stan's order (parameters, transformed parameters, GQ; column-major, 1-based),
+    values equal to the oracle's transformed parameters, and a reader round trip shaped like rstan::extract."""
+    sys.path.insert(0, ROOT)
+    from oracle import potus_oracle as po
+    sc = pkg.stancsv
+    data = datalists[year]
+    S, T = int(data["S"]), int(data["T"])
+    names = sc.column_names(data)
+    if year == 2016:
+        assert len(names) == 7 + 15098 + 15301 + 12954           # SURVEY 8(a13): ~43k doubles per draw
+        assert names[7 + 51 + 12954] == "raw_mu_c.1" and "sigma_rho" in names and "mu_e_bias" in names
+    else:
+        assert "sigma_rho" not in names and "mu_m.1" not in names and "e_bias.1" not in names
+    assert names[:8] == ["lp__", "accept_stat__", "stepsize__", "treedepth__", "n_leapfrog__", "divergent__", "energy__",
+                         "raw_mu_b_T.1"]
+    assert names[7 + S: 7 + S + 3] == ["raw_mu_b.1.1", "raw_mu_b.2.1", "raw_mu_b.3.1"]       # column-major
+    assert names[-1] == f"predicted_score.{T}.{S}" and names[-2] == f"predicted_score.{T - 1}.{S}"
+    D = po.block_layout(data)[1]
+    rng = np.random.default_rng(11)
+    chains, keep, nw, ns = 2, 2, 10, 8
+    theta = 0.3 * rng.standard_normal((chains * keep, D))
+    fit = _StubFit(data, theta, chains, keep, nw, ns)
+    paths = sc.write_stan_csv(fit, str(tmp_path), sig_figs=12)
+    assert [os.path.basename(p) for p in paths] == [f"{fit.model_name}-1.csv", f"{fit.model_name}-2.csv"]
+    out = sc.read_stan_csv(paths)
+    assert out["names"] == names
+    cfgd = out["config"]
+    assert cfgd["num_samples"] == "8" and cfgd["thin"] == "4" and cfgd["num_warmup"] == "10" and cfgd["seed"] == "1843"
+    assert cfgd["stan_version_minor"] == "24" and cfgd["model"] == fit.model_name + "_model"
+    dr = out["draws"]
+    assert dr["mu_b"].shape == (keep, chains, S, T) and dr["predicted_score"].shape == (keep, chains, T, S)
+    for c in range(chains):
+        for k in range(keep):
+            r = c * keep + k
+            fw = fit._fw[r]
+            np.testing.assert_allclose(dr["mu_b"][k, c], fw["mu_b"], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(dr["predicted_score"][k, c], po.sigmoid(fw["mu_b"]).T, atol=1e-9)
+            np.testing.assert_allclose(dr["national_mu_b_average"][k, c], fw["nat_avg"], atol=1e-9)
+            np.testing.assert_allclose(dr["national_polling_bias_average"][k, c], fw["nat_pb"], atol=1e-9)
+            np.testing.assert_allclose(dr["raw_mu_b"][k, c], fw["Z"], atol=1e-9)
+            if year == 2016:
+                np.testing.assert_allclose(dr["sigma_rho"][k, c], fw["sigma_rho"], atol=1e-9)
+                np.testing.assert_allclose(dr["rho_e_bias"][k, c], fw["rho"], atol=1e-9)
+                np.testing.assert_allclose(dr["mu_e_bias"][k, c], fw["mu_e"], atol=1e-9)
+            # kept iterations are thin*k + thin-1 of the sampling phase
+            it = nw + 4 * k + 3
+            assert abs(out["sampler_params"]["stepsize__"][k, c] - fit._sp["stepsize__"][c, it]) < 1e-9
+        np.testing.assert_allclose(out["inv_metric"][c], fit._im[c], rtol=1e-5)
+    # the likelihood through the CSV's own logit_pi columns reproduces the oracle's log density
+    th0 = theta[0]
+    lp = po.logp_grad_closed(th0, data)[0]
+    eta_s, eta_n = dr["logit_pi_democrat_state"][0, 0], dr["logit_pi_democrat_national"][0, 0]
+    ll = (np.asarray(data["n_democrat_state"]) * eta_s - np.asarray(data["n_two_share_state"]) * po.softplus(eta_s)).sum() + \
+         (np.asarray(data["n_democrat_national"]) * eta_n - np.asarray(data["n_two_share_national"]) * po.softplus(eta_n)).sum()
+    par = po.split(th0, data)
+    prior = -0.5 * sum((v ** 2).sum() for k, v in par.items() if k not in ("rho_e_bias",))
+    if year == 2016:
+        rho = po.sigmoid(par["rho_e_bias"][0])
+        prior += -0.5 * ((rho - 0.7) / 0.1) ** 2 + np.log(rho * (1 - rho))
+    assert abs((ll + prior) - lp) < 1e-6 * abs(lp)

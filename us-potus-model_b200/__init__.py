@@ -10,6 +10,7 @@ Holds only what the hot path needs:
                not in this image)
   diagnostics.py  Stan-style ESS / R-hat for the benchmark metric
   postprocess.py  the reports' election-day summaries (state table, national vote, EV simulation, Brier)
+  stancsv.py   CmdStan-format CSV writer (what rstan::read_stan_csv consumes, final_2016.R:543) + a reader for tests
   build.py     nvcc recipe
 """
 from . import datalist  # noqa: F401
@@ -17,3 +18,4 @@ from .datalist import build_datalist, synthetic_datalist, load_npz, save_npz  # 
 from .model import cmdstan_model, PotusFit, logp_grad  # noqa: F401
 from . import diagnostics  # noqa: F401
 from . import postprocess  # noqa: F401
+from . import stancsv  # noqa: F401

@@ -629,6 +629,7 @@ size_t potus_draws_size(const PotusSampler* s, const char* par) {
   const std::string p = par;
   if (p == "monitor") return (size_t)C * s->cfg.iter_sampling * (s->hm.m.S + 1);
   if (p == "sampler_params") return (size_t)C * nt * 7;
+  if (p == "inv_metric") return (size_t)C * s->hm.m.D;
   if (p == "predicted_score") return (size_t)C * s->keep * s->hm.m.S * s->hm.m.T;
   ParInfo pi;
   if (!par_info(s, par, pi) || !pi.exists) return 0;
@@ -653,6 +654,16 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
         if (k == 0) v += c0;
         if (k == 6) v -= c0;
         out[r + R * k] = v;
+      }
+    return POTUS_OK;
+  }
+  if (p == "inv_metric") {  // adapted diagonal of M^-1 per chain, [chains, D] chain-fastest, Stan parameter order
+    std::vector<float> h((size_t)C * VEC);
+    CUDA_TRY(cudaMemcpy(h.data(), s->sqrt_m, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < C; ++c)
+      for (int k = 0; k < VEC; ++k) {
+        const int si = s->hm.map_i2s[k];
+        if (si >= 0) { const double r = h[(size_t)c * VEC + k]; out[c + (size_t)C * si] = r * r; }
       }
     return POTUS_OK;
   }

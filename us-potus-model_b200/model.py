@@ -107,6 +107,17 @@ class PotusFit:
             a = a[:, self.cfg.iter_warmup:, :]
         return {k: a[:, :, i] for i, k in enumerate(SAMPLER_PARAMS)}
 
+    def inv_metric(self) -> np.ndarray:
+        """[chains, D] adapted diagonal inverse metric (CmdStan's "Diagonal elements of inverse mass matrix")."""
+        d = int(self.stats["n_params"])
+        return self._get("inv_metric").reshape((self.cfg.chains, d), order="F")
+
+    def save_csvfiles(self, directory: str, basename: str | None = None, chains=None) -> list:
+        """cmdstanr `fit$save_output_files()` / `fit$output_files()` analogue: CmdStan-format CSVs that
+        rstan::read_stan_csv parses (final_2016.R:543).  See stancsv.py."""
+        from . import stancsv
+        return stancsv.write_stan_csv(self, directory, basename, chains)
+
     def device_buffer(self, which: int):
         """(device pointer, n_floats) of a raw fp32 output buffer; bench.py wraps it for the NCCL all-gather."""
         p, n = C.c_void_p(), C.c_size_t()
