@@ -37,6 +37,7 @@ struct Ctl {
   float pad0;
   alignas(16) float kred[2][NWARP];
   alignas(16) float mred[NWARP][8];
+  alignas(16) float lred[2][3][NWARP];   // leaf reduction: |P|^2 and the two level-0 U-turn sums
   ChainState cs;
   // per-transition statistics kept by thread 0 (not needed for control flow)
   double U_samp, H_samp, U_prop, H_prop;
@@ -265,7 +266,18 @@ __device__ __forceinline__ void issue_gemm(bool b_mn_major) {
 // held in shared memory.  Called by all 512 threads.  Both mbarriers complete exactly twice per call,
 // so their phase parity is 0 for GEMM 1 and 1 for GEMM 2 on every call.
 // ================================================================================================
-__device__ __forceinline__ void eval_body(const Emit em) {
+// Leaf mode (the NUTS inner loop): the gradient never goes to TMEM; P11 continues straight into the momentum
+// update and the per-leaf bookkeeping that only needs this thread's own elements (see transition()).
+struct LeafTail {
+  float hs;          // signed half step
+  const float* Lr;   // odd leaf: momentum of the previous (even) leaf = Left_0 of the level-0 merge (+ tid), else null
+  float* Fs;         // even leaf: FIRST[...] slot that receives this leaf's momentum (+ tid), else null
+  float* Es;         // leaf closing a level-1 left half: its {e, r} slots (+ tid; e at +VEC, r at +2*VEC), else null
+  float kk, c1a, c1b;  // out: this thread's partial |P|^2 and the two level-0 U-turn dot products
+};
+
+template <bool LEAF>
+__device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
   const ModelDev& m = MD();
   Ctl& ctl = CTL();
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
@@ -427,11 +439,10 @@ __device__ __forceinline__ void eval_body(const Emit em) {
     const float* qn = sQNZ();
     const float* pbrow = scr + PB_ROW * SCR_PITCH;
     const bool full = m.full;
-    for (int k = tid; k < m.N; k += NT) {
-      const uint32_t ix = sPKI()[k];
+    // one poll: linear predictor, centred log-likelihood term f and residual r
+    auto poll_term = [&](int k, uint32_t ix, float& f, float& r, float& sigx) {
       const int s = ix & 63, d = (ix >> 6) & 255, p = (ix >> 14) & 1023, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
-      const bool nat = (s == NAT_COL);
-      const float sigx = nat ? m.sig_n : m.sig_s;
+      sigx = (s == NAT_COL) ? m.sig_n : m.sig_s;
       float eta = scr[d * SCR_PITCH + s] + pbrow[s] + m.sig_c * qn[m.nz_c + p] + sigx * qn[m.nz_x + k];
       if (full) {
         eta += m.sig_m * qn[m.nz_m + mo] + m.sig_pop * qn[m.nz_pop + po];
@@ -439,7 +450,6 @@ __device__ __forceinline__ void eval_body(const Emit em) {
       }
       const float n = sPKF(1)[k], eh = sPKF(2)[k], ph = sPKF(3)[k], rh = sPKF(4)[k];
       const float dl = eta - eh;
-      float f, r;
       if (fabsf(dl) < 12.0f) {
         // ll(eta) - ll(eta_hat) = n [ (y/n) dl - log1p(p_hat expm1(dl)) ],  y/n = p_hat + rho_hat
         const float em1 = expm1f(dl);
@@ -453,16 +463,40 @@ __device__ __forceinline__ void eval_body(const Emit em) {
         f = n * ((ph + rh) * dl - (sp - sph));
         r = n * ((ph + rh) - sg);
       }
+    };
+    auto poll_accum = [&](int k, uint32_t ix, float f, float r, float sigx) {
+      const int s = ix & 63, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
       fsum += f;
       sRR()[k] = r;
       sGNZ()[m.nz_x + k] = sigx * r;
-      if (nat) rnat += r;
+      if (s == NAT_COL) rnat += r;
       if (full) {
 #pragma unroll
         for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
         gm[MAX_MODE - 1] += r;  // total; the last class follows by difference
       }
+    };
+#ifdef POTUS_POLL2
+    // two independent polls per trip: their dependent chains (index -> gathers -> expm1/log1p/divide) interleave
+    for (int k = tid; k < m.N; k += 2 * NT) {
+      const int k2 = k + NT;
+      const bool has2 = k2 < m.N;
+      const int k2c = has2 ? k2 : k;
+      const uint32_t ix = sPKI()[k], ix2 = sPKI()[k2c];
+      float f, r, sx, f2, r2, sx2;
+      poll_term(k, ix, f, r, sx);
+      poll_term(k2c, ix2, f2, r2, sx2);
+      poll_accum(k, ix, f, r, sx);
+      if (has2) poll_accum(k2, ix2, f2, r2, sx2);
     }
+#else
+    for (int k = tid; k < m.N; k += NT) {
+      const uint32_t ix = sPKI()[k];
+      float f, r, sx;
+      poll_term(k, ix, f, r, sx);
+      poll_accum(k, ix, f, r, sx);
+    }
+#endif
     PROF(16);
     double v0 = 0.5 * (double)qsq - (double)fsum;
 #pragma unroll
@@ -675,28 +709,39 @@ __device__ __forceinline__ void eval_body(const Emit em) {
   }
   __syncthreads();  // S8
   PROF(9);
-  // ---------------- P11: gradient of U in owner layout -> TMEM
+  // ---------------- P11: gradient of U in owner layout
   {
     const uint32_t tp = tpriv();
     float carry0 = 0.f, carry1 = 0.f;
-    if (zlane)
+    if (zlane) {
 #pragma unroll
       for (int w2 = 0; w2 < NWARP - 1; ++w2) {
         const float2 t2 = *reinterpret_cast<const float2*>(sTOT() + w2 * 52 + 2 * l);
         if (w2 < w) { carry0 += t2.x; carry1 += t2.y; }
       }
+    }
     const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
     const float* gn = sGNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
     const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
     const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
     float pre0 = carry0, pre1 = carry1;   // running prefix of H over days (this warp's rows)
+    float kk = 0.f, c1a = 0.f, c1b = 0.f;
+    // 8-element chunks: four operand sets (g, p_half, s, previous momentum) live at once stay inside the register budget
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float g[16];
+    for (int c = 0; c < 4; ++c) {
+      float g[8], p[8], sm[8], lr[8];
+      if (LEAF) {
+        ptx::tmem_ld8f(tp + TM_P + 8 * c, p);
+        ptx::tmem_ld8f(tp + TM_S + 8 * c, sm);
+        if (lt.Lr != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) lr[j] = lt.Lr[(c * 8 + j) * NT];
+        }
+      }
       if (zlane) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const int d = (h * 16 + j) >> 1;
+        for (int j = 0; j < 8; j += 2) {
+          const int d = (c * 8 + j) >> 1;
           const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
           if (d < nd) { pre0 += hz[d * SCR_PITCH]; pre1 += hz[d * SCR_PITCH + 1]; }
           const bool walk = d < ndw;
@@ -705,16 +750,43 @@ __device__ __forceinline__ void eval_body(const Emit em) {
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 th = *reinterpret_cast<const float4*>(qn + h * 16 + j);
-          const float4 gs = *reinterpret_cast<const float4*>(gn + h * 16 + j);
+        for (int j = 0; j < 8; j += 4) {
+          const float4 th = *reinterpret_cast<const float4*>(qn + c * 8 + j);
+          const float4 gs = *reinterpret_cast<const float4*>(gn + c * 8 + j);
           g[j] = th.x - gs.x; g[j + 1] = th.y - gs.y; g[j + 2] = th.z - gs.z; g[j + 3] = th.w - gs.w;
         }
       }
       __syncwarp();
-      tm_st16(tp, TM_G + 16 * h, g);
+      if (!LEAF) {
+        ptx::tmem_st8f(tp + TM_G + 8 * c, g);
+      } else {
+        // full-step momentum P = p_half - hs*s*g (kept in TM_TMP for the U-turn merges), next half-step momentum
+        // p_half' = 2P - p_half, |P|^2, and -- for an odd leaf -- the level-0 merge with the previous leaf
+        ptx::tmem_wait_ld();
+        const bool odd = lt.Lr != nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float P = fmaf(-lt.hs * sm[j], g[j], p[j]);
+          kk = fmaf(P, P, kk);
+          if (odd) { const float x = lr[j] + P; c1a = fmaf(lr[j], x, c1a); c1b = fmaf(P, x, c1b); }
+          p[j] = 2.0f * P - p[j];
+          g[j] = P;
+        }
+        ptx::tmem_st8f(tp + TM_TMP + 8 * c, g);
+        ptx::tmem_st8f(tp + TM_P + 8 * c, p);
+        if (odd) ptx::tmem_st8f(tp + TM_G + 8 * c, lr);   // running sum of left rhos for the higher merges
+        if (lt.Fs != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) lt.Fs[(c * 8 + j) * NT] = g[j];
+        }
+        if (lt.Es != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { lt.Es[VEC + (c * 8 + j) * NT] = g[j]; lt.Es[2 * VEC + (c * 8 + j) * NT] = g[j] + lr[j]; }
+        }
+      }
     }
     ptx::tmem_wait_st();
+    if (LEAF) { lt.kk = kk; lt.c1a = c1a; lt.c1b = c1b; }
   }
   PROF(10);
   // note: callers synchronise before reading ctl.U
@@ -722,7 +794,7 @@ __device__ __forceinline__ void eval_body(const Emit em) {
 
 // out-of-line copy for the cold call sites (initial point of a transition, step-size search, inits, final draw);
 // the leaf loop of transition() inlines eval_body so that registers are allocated across the whole loop body
-__device__ __noinline__ void eval_point(const Emit em) { eval_body(em); }
+__device__ __noinline__ void eval_point(const Emit em) { LeafTail none{}; eval_body<false>(em, none); }
 
 // ================================================================================================
 // small block-wide helpers
@@ -778,54 +850,31 @@ __device__ __forceinline__ float full_step_momentum(uint32_t tp, float hs) {
   ptx::tmem_wait_st();
   return ss;
 }
-// Phase C: p_half' = 2P - p_half ; q' = q + eps_signed * s * p_half'
-__device__ __forceinline__ void advance(uint32_t tp, float eps_signed) {
+// position update of a leaf: q' = q + eps_signed * s * p_half'   (p_half' was written to TM_P by the fused leaf tail)
+__device__ __forceinline__ void advance_q(uint32_t tp, float eps_signed) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    float p[16], s[16], P[16];
+    float p[16], s[16];
     tm_ld16_nowait(tp, TM_P + 16 * h, p);
     tm_ld16_nowait(tp, TM_S + 16 * h, s);
-    tm_ld16_nowait(tp, TM_TMP + 16 * h, P);
     ptx::tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-      p[j] = 2.0f * P[j] - p[j];
-      p[j + 1] = 2.0f * P[j + 1] - p[j + 1];
       float2* q = qpair((h * 16 + j) >> 1);
       float2 v = *q;
       v.x = fmaf(eps_signed * s[j], p[j], v.x);
       v.y = fmaf(eps_signed * s[j + 1], p[j + 1], v.y);
       *q = v;
     }
-    tm_st16(tp, TM_P + 16 * h, p);
   }
-  ptx::tmem_wait_st();
 }
 
 // One U-turn merge (Stan's three criteria) between the completed left subtree L = {b,e,r} and the
 // implicit right subtree R = {b: rb (or P if null), r: P + S, e: P}; S (TM_G) += L.r afterwards.
-// `first` : S is implicitly zero.   `single`: L.b = L.e = L.r (Left_0).
-__device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first,
-                                            bool single) {
+// `first` : S is implicitly zero.  (Level 0, where L is a single leaf, is fused into the leaf tail.)
+__device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first) {
   const int tid = threadIdx.x;
   float c1a = 0.f, c1b = 0.f, c2a = 0.f, c2b = 0.f, c3a = 0.f, c3b = 0.f;
-  if (single) {
-    // Left_0 = one leaf `a`, right = this leaf: rho = a + P and the three criteria reduce to a.(a+P) > 0, P.(a+P) > 0
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      float P[16], S[16];
-      tm_ld16(tp, TM_TMP + 16 * h, P);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float lr = Lr[(h * 16 + j) * NT + tid];
-        const float x = lr + P[j];
-        c1a = fmaf(lr, x, c1a); c1b = fmaf(P[j], x, c1b);
-        S[j] = lr;
-      }
-      tm_st16(tp, TM_G + 16 * h, S);
-    }
-    c2a = c3a = 1.f; c2b = c3b = 1.f;
-  } else
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float P[16], S[16];
@@ -962,10 +1011,62 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
     for (int n = 0; n < nleaf; ++n) {
       const Emit none{nullptr, nullptr, nullptr};
       PROF_DECL;
-      eval_body(none);
+      // FIRST[z] holds the momentum of the first leaf of every live subtree: leaf m goes to slot z = tz(m)
+      // (m = 0: z = depth).  It is not overwritten before leaf m + 2^(z+1), i.e. after every subtree that
+      // starts at m has been merged -- so left summaries need no copy of their first momentum.
+      auto first_slot = [&](int mleaf) -> float* {
+        const int z = mleaf ? (__ffs(mleaf) - 1) : depth;
+        return slot_ptr(ws, SLOT_LEFT + 3 * (z - 1));
+      };
+      const int t = __ffs(~n) - 1;  // trailing ones of n = number of subtrees this leaf completes
+      const bool last = (n == nleaf - 1);
+      // gradient + momentum update + everything that needs only this thread's elements, in one sweep:
+      //   even leaf: its momentum starts subtrees at levels 0..tz(n) -> FIRST slot;
+      //   odd leaf : level-0 U-turn sums against the previous leaf; if it closes a level-1 left half (t == 1), its {e, r}
+#ifdef POTUS_PREF
+      // checkpoints of levels >= 2 were written >= 4 leaves ago and may have left L2 (148 CTAs x 2.4 MB of slots):
+      // pull the ones this leaf's merges will read back in while the gradient is computed
+      if (tid == 0 && t >= 3) {
+        for (int k = 2; k < t; ++k) {
+          const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
+          for (int part = 0; part < 4; ++part) {
+            ptx::prefetch_l2_bulk(Lk + VEC + part * (VEC / 4), VEC);
+            ptx::prefetch_l2_bulk(Lk + 2 * VEC + part * (VEC / 4), VEC);
+            ptx::prefetch_l2_bulk(first_slot(n - (2 << k) + 1) + part * (VEC / 4), VEC);
+            ptx::prefetch_l2_bulk(first_slot(n - (1 << k) + 1) + part * (VEC / 4), VEC);
+          }
+        }
+      }
+#endif
+      LeafTail lt;
+      lt.hs = hs;
+      lt.Lr = (t > 0) ? first_slot(n - 1) + tid : nullptr;
+      lt.Fs = (t == 0 && !last) ? first_slot(n) + tid : nullptr;
+      lt.Es = (t == 1 && !last) ? slot_ptr(ws, SLOT_LEFT) + tid : nullptr;
+      eval_body<true>(none, lt);
       PROF_RESET;
-      float kk = full_step_momentum(tp, hs);
-      kk = block_sum_f(kk, n & 1);
+      // one block reduction for |P|^2 and the two level-0 criteria (its barrier also publishes ctl.U)
+      float kk = lt.kk, c1a = lt.c1a, c1b = lt.c1b;
+      {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          kk += __shfl_xor_sync(0xffffffffu, kk, off);
+          c1a += __shfl_xor_sync(0xffffffffu, c1a, off);
+          c1b += __shfl_xor_sync(0xffffffffu, c1b, off);
+        }
+        float* r3 = &ctl.lred[n & 1][0][0];
+        if ((tid & 31) == 0) { r3[tid >> 5] = kk; r3[NWARP + (tid >> 5)] = c1a; r3[2 * NWARP + (tid >> 5)] = c1b; }
+        __syncthreads();
+        float tot[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float4 a4 = *reinterpret_cast<const float4*>(r3 + i * NWARP), b4 = *reinterpret_cast<const float4*>(r3 + i * NWARP + 4);
+          const float4 c4 = *reinterpret_cast<const float4*>(r3 + i * NWARP + 8), d4 = *reinterpret_cast<const float4*>(r3 + i * NWARP + 12);
+          tot[i] = (((a4.x + a4.y) + (a4.z + a4.w)) + ((b4.x + b4.y) + (b4.z + b4.w))) +
+                   (((c4.x + c4.y) + (c4.z + c4.w)) + ((d4.x + d4.y) + (d4.z + d4.w)));
+        }
+        kk = tot[0]; c1a = tot[1]; c1b = tot[2];
+      }
       PROF(11);
       double h = ctl.U + 0.5 * (double)kk;
       if (!(h == h)) h = CUDART_INF;
@@ -985,31 +1086,21 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         }
       }
       PROF(12);
-      // U-turn checks for every subtree this leaf completes
-      const int t = __ffs(~n) - 1;  // trailing ones of n
-      // FIRST[z] holds the momentum of the first leaf of every live subtree: leaf m goes to slot z = tz(m)
-      // (m = 0: z = depth).  It is not overwritten before leaf m + 2^(z+1), i.e. after every subtree that
-      // starts at m has been merged -- so left summaries need no copy of their first momentum.
-      auto first_slot = [&](int mleaf) -> float* {
-        const int z = mleaf ? (__ffs(mleaf) - 1) : depth;
-        return slot_ptr(ws, SLOT_LEFT + 3 * (z - 1));
-      };
-      for (int k = 0; k < t && ok; ++k) {
-        if (k == 0) {
-          const float* L0p = first_slot(n - 1);   // the previous (even) leaf
-          ok = merge_check(tp, L0p, L0p, L0p, nullptr, true, true);
-        } else {
-          const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
-          ok = merge_check(tp, first_slot(n - (2 << k) + 1), Lk + VEC, Lk + 2 * VEC, first_slot(n - (1 << k) + 1), false, false);
-        }
+      // position update q' = q + eps*s*p_half' (after the candidate copy above; each thread touches only its own
+      // elements, and the first cross-thread read of q comes after barrier S1 of the next gradient)
+      advance_q(tp, eps_s);
+      PROF(15);
+      // U-turn checks for every subtree this leaf completes (level 0 came with the reduction above)
+      if (t > 0) ok = (c1a > 0.f) && (c1b > 0.f);
+      for (int k = 1; k < t && ok; ++k) {
+        const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
+        ok = merge_check(tp, first_slot(n - (2 << k) + 1), Lk + VEC, Lk + 2 * VEC, first_slot(n - (1 << k) + 1), false);
       }
       if (!ok) break;
       PROF(13);
-      if (n < nleaf - 1) {
-        if (t == 0) {
-          tm_to_global(tp, TM_TMP, first_slot(n));   // an even leaf starts subtrees at levels 0..tz(n)
-        } else {
-          // this subtree becomes the stored left half at level t: {e, r} (its b is FIRST[...])
+      if (!last) {
+        if (t >= 2) {
+          // this subtree becomes the stored left half at level t: {e, r} (its b is FIRST[...]); t == 1 was stored above
           float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1)) + tid;
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -1031,7 +1122,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         const float* F = slot_ptr(ws, dir > 0 ? SLOT_TOP_BB : SLOT_TOP_FF);
         const float* A = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB);
         const float* Rb = (depth == 0) ? nullptr : first_slot(0);
-        persist = merge_check(tp, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0, false);
+        persist = merge_check(tp, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0);
         float* rho = slot_ptr(ws, SLOT_TOP_RHO) + tid;
         float* endv = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB) + tid;
 #pragma unroll
@@ -1049,10 +1140,6 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         }
       }
       PROF(14);
-      advance(tp, eps_s);
-      // no barrier here: the next phase (P1 of the next leaf, or the end-of-subtree bookkeeping) only touches the
-      // calling thread's own position elements; the first cross-thread read of q comes after barrier S1
-      PROF(15);
       if (threadIdx.x == 0) { PROF_COUNT; }
     }
     if (!ok) break;

@@ -172,6 +172,11 @@ __device__ __forceinline__ void tmem_st16f(uint32_t taddr, const float (&v)[16])
 }
 
 
+// bulk L2 prefetch of a global range (bytes: multiple of 16)
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
+
 // 8-column variants (thread-private half vectors; keep register pressure low at 1024 threads / 64 regs)
 __device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
