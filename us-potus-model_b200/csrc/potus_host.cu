@@ -365,7 +365,7 @@ int build_model(const PotusData* d, HostModel& hm) {
         int s = 2 * l + (e & 1), t = DPW * wq + (e >> 1);
         if (s < S && t < T) idx = o.Z + s + S * t;
       } else {
-        int k = (wq * NZ_LANES + (l - ZLANES)) * EPT + e;
+        int k = nz_slot(wq, l - ZLANES, e);
         if (k < m.NZ) {
           if (k < m.nz_c) idx = o.zT + (k - m.nz_zT);
           else if (k < m.nz_c + P) idx = o.c + (k - m.nz_c);

@@ -85,11 +85,11 @@ __device__ __forceinline__ uint32_t tpriv() {
   return CTL().tmem_base + (((w & 3u) * 32u) << 16) + (w >> 2) * 32u;
 }
 // owned position elements come in 16 float2 pairs: pair d of a walk lane = states (2l,2l+1) on day 16w+d;
-// pair d of an nz lane = nz slots nz0+2d, nz0+2d+1.
+// pair d of an nz lane = nz slots nz_slot(w, ln, 2d), +1 (see potus_layout.h).
 __device__ __forceinline__ float2* qpair(int d) {
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   if (l < ZLANES) return reinterpret_cast<float2*>(sQZ() + (16 * w + d) * QZ_PITCH + 2 * l);
-  return reinterpret_cast<float2*>(sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT + 2 * d);
+  return reinterpret_cast<float2*>(sQNZ() + nz_slot(w, l - ZLANES, 2 * d));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -198,12 +198,13 @@ __device__ __forceinline__ void tmem_epilogue(float scale, bool add_prior, uint3
   ptx::tmem_ld16f(taddr + TM_D2, d2);
   ptx::tmem_wait_ld();
   if (tile == 0) ptx::mbar_wait(&ctl.bar_mma[1], parity);
+  float2* out2 = reinterpret_cast<float2*>(out);   // (row*54 + 32*half) is even: 8-byte aligned
   if (rowok) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
-      if (prior_row) v += pr[j];
-      out[j] = v;
+    for (int j = 0; j < 16; j += 2) {
+      float v0 = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale, v1 = fmaf(d2[j + 1], 1.0f / 2048.0f, d1[j + 1]) * scale;
+      if (prior_row) { v0 += pr[j]; v1 += pr[j + 1]; }
+      out2[j >> 1] = make_float2(v0, v1);
     }
   }
   // second 16 columns: half 0 -> cols 16..31, half 1 -> cols 48..63 of which only 48..51 exist
@@ -213,17 +214,17 @@ __device__ __forceinline__ void tmem_epilogue(float scale, bool add_prior, uint3
   if (rowok) {
     if (half == 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
-        if (prior_row) v += pr[16 + j];
-        out[16 + j] = v;
+      for (int j = 0; j < 16; j += 2) {
+        float v0 = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale, v1 = fmaf(d2[j + 1], 1.0f / 2048.0f, d1[j + 1]) * scale;
+        if (prior_row) { v0 += pr[16 + j]; v1 += pr[16 + j + 1]; }
+        out2[8 + (j >> 1)] = make_float2(v0, v1);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float v = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale;
-        if (prior_row) v += pr[16 + j];
-        out[16 + j] = v;
+      for (int j = 0; j < 4; j += 2) {
+        float v0 = fmaf(d2[j], 1.0f / 2048.0f, d1[j]) * scale, v1 = fmaf(d2[j + 1], 1.0f / 2048.0f, d1[j + 1]) * scale;
+        if (prior_row) { v0 += pr[16 + j]; v1 += pr[16 + j + 1]; }
+        out2[8 + (j >> 1)] = make_float2(v0, v1);
       }
     }
   }
@@ -302,16 +303,13 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
     }
     *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
   } else {
-    const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
+    const float* qn = sQNZ() + nz_slot(w, l - ZLANES, 0);
 #pragma unroll
-    for (int e = 0; e < EPT; e += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(qn + e);
-      qsq += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int d = 0; d < 16; ++d) {
+      const float2 v = *reinterpret_cast<const float2*>(qn - d * (2 * NZ_LANES));
+      qsq = fmaf(v.x, v.x, fmaf(v.y, v.y, qsq));
     }
-    if (m.full) {  // rho's unconstrained value carries no N(0,1) term
-      const int k = m.nz_urho - (w * NZ_LANES + (l - ZLANES)) * EPT;
-      if (k >= 0 && k < EPT) { const float v = sQNZ()[m.nz_urho]; qsq -= v * v; }
-    }
+    if (m.full && tid == ZLANES) { const float v = sQNZ()[m.nz_urho]; qsq -= v * v; }  // rho's unconstrained value carries no N(0,1) term
   }
   __syncthreads();  // S1
   PROF(0);
@@ -476,27 +474,12 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
         gm[MAX_MODE - 1] += r;  // total; the last class follows by difference
       }
     };
-#ifdef POTUS_POLL2
-    // two independent polls per trip: their dependent chains (index -> gathers -> expm1/log1p/divide) interleave
-    for (int k = tid; k < m.N; k += 2 * NT) {
-      const int k2 = k + NT;
-      const bool has2 = k2 < m.N;
-      const int k2c = has2 ? k2 : k;
-      const uint32_t ix = sPKI()[k], ix2 = sPKI()[k2c];
-      float f, r, sx, f2, r2, sx2;
-      poll_term(k, ix, f, r, sx);
-      poll_term(k2c, ix2, f2, r2, sx2);
-      poll_accum(k, ix, f, r, sx);
-      if (has2) poll_accum(k2, ix2, f2, r2, sx2);
-    }
-#else
     for (int k = tid; k < m.N; k += NT) {
       const uint32_t ix = sPKI()[k];
       float f, r, sx;
       poll_term(k, ix, f, r, sx);
       poll_accum(k, ix, f, r, sx);
     }
-#endif
     PROF(16);
     double v0 = 0.5 * (double)qsq - (double)fsum;
 #pragma unroll
@@ -699,13 +682,22 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
     const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
 #pragma unroll
     for (int d = 0; d < 16; ++d)
-      if (d < nd) { run0 += hz[d * SCR_PITCH]; run1 += hz[d * SCR_PITCH + 1]; }
+      if (d < nd) { const float2 hh = *reinterpret_cast<const float2*>(hz + d * SCR_PITCH); run0 += hh.x; run1 += hh.y; }
     *reinterpret_cast<float2*>(sTOT() + w * 52 + 2 * l) = make_float2(run0, run1);
   }
   if (tid < S) {  // gradient sources of raw_mu_b_T and raw_polling_bias share the spare GEMM row
     const float h = sSCR()[PB_ROW * SCR_PITCH + tid];
     sGNZ()[m.nz_zT + tid] = m.a_T * h;
     sGNZ()[m.nz_zb + tid] = m.a_b * h;
+  }
+  // odd leaf: the previous leaf's momentum (level-0 merge partner) is fetched from L2 now, so that its latency hides
+  // behind barrier S8 and the carry loads instead of stalling the sweep below
+  float lrv[EPT];
+  if (LEAF) {
+    if (lt.Lr != nullptr) {
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) lrv[e] = lt.Lr[e * NT];
+    }
   }
   __syncthreads();  // S8
   PROF(9);
@@ -720,8 +712,8 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
         if (w2 < w) { carry0 += t2.x; carry1 += t2.y; }
       }
     }
-    const float* qn = sQNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
-    const float* gn = sGNZ() + (w * NZ_LANES + (l - ZLANES)) * EPT;
+    const float* qn = sQNZ() + nz_slot(w, l - ZLANES, 0);
+    const float* gn = sGNZ() + nz_slot(w, l - ZLANES, 0);
     const float* qz = sQZ() + (16 * w) * QZ_PITCH + 2 * l;
     const float* hz = sSCR() + (16 * w) * SCR_PITCH + 2 * l;
     float pre0 = carry0, pre1 = carry1;   // running prefix of H over days (this warp's rows)
@@ -733,27 +725,26 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
       if (LEAF) {
         ptx::tmem_ld8f(tp + TM_P + 8 * c, p);
         ptx::tmem_ld8f(tp + TM_S + 8 * c, sm);
-        if (lt.Lr != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) lr[j] = lt.Lr[(c * 8 + j) * NT];
-        }
+        for (int j = 0; j < 8; ++j) lr[j] = lrv[c * 8 + j];
       }
       if (zlane) {
 #pragma unroll
         for (int j = 0; j < 8; j += 2) {
           const int d = (c * 8 + j) >> 1;
           const float2 z = *reinterpret_cast<const float2*>(qz + d * QZ_PITCH);
-          if (d < nd) { pre0 += hz[d * SCR_PITCH]; pre1 += hz[d * SCR_PITCH + 1]; }
+          if (d < nd) { const float2 hh = *reinterpret_cast<const float2*>(hz + d * SCR_PITCH); pre0 += hh.x; pre1 += hh.y; }
           const bool walk = d < ndw;
           g[j] = walk ? fmaf(-m.a_w, pre0, z.x) : z.x;
           g[j + 1] = walk ? fmaf(-m.a_w, pre1, z.y) : z.y;
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 th = *reinterpret_cast<const float4*>(qn + c * 8 + j);
-          const float4 gs = *reinterpret_cast<const float4*>(gn + c * 8 + j);
-          g[j] = th.x - gs.x; g[j + 1] = th.y - gs.y; g[j + 2] = th.z - gs.z; g[j + 3] = th.w - gs.w;
+        for (int j = 0; j < 8; j += 2) {
+          const int d = (c * 8 + j) >> 1;
+          const float2 th = *reinterpret_cast<const float2*>(qn - d * (2 * NZ_LANES));
+          const float2 gs = *reinterpret_cast<const float2*>(gn - d * (2 * NZ_LANES));
+          g[j] = th.x - gs.x; g[j + 1] = th.y - gs.y;
         }
       }
       __syncwarp();
@@ -1023,7 +1014,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       // gradient + momentum update + everything that needs only this thread's elements, in one sweep:
       //   even leaf: its momentum starts subtrees at levels 0..tz(n) -> FIRST slot;
       //   odd leaf : level-0 U-turn sums against the previous leaf; if it closes a level-1 left half (t == 1), its {e, r}
-#ifdef POTUS_PREF
+#ifndef POTUS_NO_PREF
       // checkpoints of levels >= 2 were written >= 4 leaves ago and may have left L2 (148 CTAs x 2.4 MB of slots):
       // pull the ones this leaf's merges will read back in while the gradient is computed
       if (tid == 0 && t >= 3) {

@@ -20,7 +20,8 @@ constexpr int MAX_S = 51, MAX_T = 254;  // rows 254/255 of the 256-row MMA tile:
 constexpr int PB_ROW = 254;
 constexpr int NAT_COL = 51;             // GEMM column / K-slot that carries the national series
 constexpr int ROWS = 256, KPAD = 64;
-constexpr int SCR_PITCH = 53;           // fp32 scratch pitch (odd: conflict-free row-per-lane access)
+constexpr int SCR_PITCH = 54;           // fp32 scratch pitch: even, so a lane's state pair is one 8-byte access, and
+                                        // 54 = 22 (mod 32) keeps row-per-lane float2 stores conflict-free per half-warp
 constexpr int QZ_PITCH = 52;            // q walk block [t][52] (float2 per state pair)
 constexpr int NPOLL_CAP = 1664;
 constexpr int SEG = 16;                 // polls per level-1 segment (fully unrolled, predicated)
@@ -77,6 +78,15 @@ constexpr int SLOT_ENDF_Q = 31, SLOT_ENDF_P = 32, SLOT_ENDB_Q = 33, SLOT_ENDB_P 
 constexpr int SLOT_CAND_A = 35, SLOT_CAND_B = 36; // sample / proposal positions (roles swap)
 constexpr int SLOT_TMPQ = 37;
 constexpr int NSLOT = 38;
+
+// nz ownership: warp w owns nz slots [192w, 192w+192); inside, lane ln (0..5) owns the float2 pairs (15-d)*6+ln, d = 0..15,
+// so that the six nz lanes of a warp touch 12 consecutive words whenever they walk their elements in step
+// (a [lane][32] block layout would put all six on the same banks).  The reversal in d places those 12 words on exactly
+// the banks that the 26 walk lanes' 52 words (q walk block, pitch 52) use only once: 12(15-d) = 20d+20 (mod 32), so a
+// warp-wide float2 access to "pair d" of every lane is two wavefronts.
+__host__ __device__ inline int nz_slot(int w, int ln, int e) {
+  return w * (NZ_LANES * EPT) + ((15 - (e >> 1)) * NZ_LANES + ln) * 2 + (e & 1);
+}
 
 // ---- packed poll index: s[0:6) d[6:14) p[14:24) m[24:27) o[27:30) unadj[30]
 __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o, int un) {
