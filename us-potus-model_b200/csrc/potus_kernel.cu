@@ -273,7 +273,7 @@ struct LeafTail {
   float hs;          // signed half step
   const float* Lr;   // odd leaf: momentum of the previous (even) leaf = Left_0 of the level-0 merge (+ tid), else null
   float* Fs;         // even leaf: FIRST[...] slot that receives this leaf's momentum (+ tid), else null
-  float* Es;         // leaf closing a level-1 left half: its {e, r} slots (+ tid; e at +VEC, r at +2*VEC), else null
+  float* Es;         // leaf closing a level-1 left half: its e slot (+ tid; e at +VEC), else null
   float kk, c1a, c1b;  // out: this thread's partial |P|^2 and the two level-0 U-turn dot products
 };
 
@@ -772,7 +772,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
         }
         if (lt.Es != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { lt.Es[VEC + (c * 8 + j) * NT] = g[j]; lt.Es[2 * VEC + (c * 8 + j) * NT] = g[j] + lr[j]; }
+          for (int j = 0; j < 8; ++j) lt.Es[VEC + (c * 8 + j) * NT] = g[j];   // (its r = b + e is re-formed by the level-1 merge)
         }
       }
     }
@@ -863,7 +863,10 @@ __device__ __forceinline__ void advance_q(uint32_t tp, float eps_signed) {
 // One U-turn merge (Stan's three criteria) between the completed left subtree L = {b,e,r} and the
 // implicit right subtree R = {b: rb (or P if null), r: P + S, e: P}; S (TM_G) += L.r afterwards.
 // `first` : S is implicitly zero.  (Level 0, where L is a single leaf, is fused into the leaf tail.)
-__device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first) {
+// `level1`: both halves are two leaves: L.r = L.b + L.e (the same fp32 sum that would have been stored) and R.b = S
+// (the previous leaf, put there by the level-0 merge), so only two vectors come from global memory.
+__device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first,
+                                            bool level1 = false) {
   const int tid = threadIdx.x;
   float c1a = 0.f, c1b = 0.f, c2a = 0.f, c2b = 0.f, c3a = 0.f, c3b = 0.f;
 #pragma unroll
@@ -880,10 +883,10 @@ __device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const 
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int gi = (h * 16 + j) * NT + tid;
-      const float lr = Lr[gi];
       const float lb = Lb[gi];
       const float le = Le[gi];
-      const float rb = (Rb == nullptr) ? P[j] : Rb[gi];
+      const float lr = level1 ? le + lb : Lr[gi];
+      const float rb = level1 ? S[j] : ((Rb == nullptr) ? P[j] : Rb[gi]);
       const float x = lr + S[j] + P[j];
       c1a = fmaf(lb, x, c1a); c1b = fmaf(P[j], x, c1b);
       const float y = lr + rb;
@@ -1083,7 +1086,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       PROF(15);
       // U-turn checks for every subtree this leaf completes (level 0 came with the reduction above)
       if (t > 0) ok = (c1a > 0.f) && (c1b > 0.f);
-      for (int k = 1; k < t && ok; ++k) {
+      if (t > 1 && ok) ok = merge_check(tp, first_slot(n - 3), slot_ptr(ws, SLOT_LEFT) + VEC, nullptr, nullptr, false, true);
+      for (int k = 2; k < t && ok; ++k) {
         const float* Lk = slot_ptr(ws, SLOT_LEFT + 3 * (k - 1));
         ok = merge_check(tp, first_slot(n - (2 << k) + 1), Lk + VEC, Lk + 2 * VEC, first_slot(n - (1 << k) + 1), false);
       }
