@@ -190,3 +190,19 @@ def test_posterior_matches_reference_tables_2012_no_mode(pkg, datalists, cuda_li
     ora = json.load(open(os.path.join(GOLDEN, "oracle_posterior_2012.json")))
     z = np.abs(mean - np.array(ora["mean"])) / (4 * np.array(ora["mcse"]) + 5e-4)
     assert z.max() <= 1.0, z.max()
+
+
+def test_same_seed_same_binary_is_bit_reproducible(pkg, datalists, cuda_lib):
+    """Two runs of one binary with one seed must agree bit for bit (no atomics, fixed reduction trees).  Added after an
+    unchanged build was seen to give two different n_leapfrog totals (profiles/r01_d_ab4.log)."""
+    d = datalists[2016]
+    runs = []
+    for _ in range(3):
+        fit = pkg.cmdstan_model("poll_model_2020.stan").sample(data=d, seed=1843, chains=148, iter_warmup=40, iter_sampling=10,
+                                                               keep_per_chain=1)
+        sp = fit.sampler_params()
+        runs.append({k: v.copy() for k, v in sp.items()})
+        fit.close()
+    for r in runs[1:]:
+        for k in runs[0]:
+            assert np.array_equal(runs[0][k], r[k]), f"{k} differs between identical runs"

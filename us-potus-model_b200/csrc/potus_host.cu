@@ -378,7 +378,7 @@ int build_model(const PotusData* d, HostModel& hm) {
           else idx = o.zb + (k - m.nz_zb);
         }
       }
-      hm.map_i2s[e * NT + tid] = idx;
+      hm.map_i2s[oslot(e, tid)] = idx;
     }
   }
   {  // every Stan index must be covered exactly once

@@ -130,43 +130,55 @@ __device__ __forceinline__ void tm_st16(uint32_t tp, uint32_t col, const float (
 __device__ __forceinline__ void tm_ld16_nowait(uint32_t tp, uint32_t col, float (&v)[16]) { ptx::tmem_ld16f(tp + col, v); }
 __device__ __forceinline__ float* slot_ptr(float* ws, int slot) { return ws + (size_t)slot * VEC; }
 
+// ---- owner-layout vectors in global memory (potus_layout.h: oslot): float4 group k of the calling thread
+__device__ __forceinline__ float4* own4(float* vec) { return reinterpret_cast<float4*>(vec) + threadIdx.x; }
+__device__ __forceinline__ const float4* own4(const float* vec) { return reinterpret_cast<const float4*>(vec) + threadIdx.x; }
+// (group k of the thread = own4(vec)[k * NT], k = 0..7)
+__device__ __forceinline__ void st_groups4(float4* o, int k0, const float* v, int n) {   // n floats (multiple of 4) -> groups k0..
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * i < n) o[(k0 + i) * NT] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+__device__ __forceinline__ void ld_groups4(const float4* o, int k0, float* v, int n) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (4 * i < n) { const float4 t = o[(k0 + i) * NT]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+}
+
 __device__ __forceinline__ void tm_to_global(uint32_t tp, uint32_t col, float* g) {
-  g += threadIdx.x;
+  float4* o = own4(g);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
     tm_ld16(tp, col + 16 * h, v);
-#pragma unroll
-    for (int j = 0; j < 16; ++j) g[(h * 16 + j) * NT] = v[j];
+    st_groups4(o, 4 * h, v, 16);
   }
 }
 __device__ __forceinline__ void global_to_tm(uint32_t tp, uint32_t col, const float* g) {
-  g += threadIdx.x;
+  const float4* o = own4(g);
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = g[(h * 16 + j) * NT];
+    ld_groups4(o, 4 * h, v, 16);
     tm_st16(tp, col + 16 * h, v);
   }
   ptx::tmem_wait_st();
 }
 __device__ __forceinline__ void q_to_global(float* g) {
-  g += threadIdx.x;
+  float4* o = own4(g);
 #pragma unroll
-  for (int d = 0; d < 16; ++d) {
-    const float2 v = *qpair(d);
-    g[(2 * d) * NT] = v.x;
-    g[(2 * d + 1) * NT] = v.y;
+  for (int k = 0; k < 8; ++k) {
+    const float2 a = *qpair(2 * k), b = *qpair(2 * k + 1);
+    o[k * NT] = make_float4(a.x, a.y, b.x, b.y);
   }
 }
 __device__ __forceinline__ void global_to_q(const float* g) {
-  g += threadIdx.x;
-  float2 v[16];
+  const float4* o = own4(g);
+  float4 v[8];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) { v[d].x = g[(2 * d) * NT]; v[d].y = g[(2 * d + 1) * NT]; }
+  for (int k = 0; k < 8; ++k) v[k] = o[k * NT];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) *qpair(d) = v[d];
+  for (int k = 0; k < 8; ++k) { *qpair(2 * k) = make_float2(v[k].x, v[k].y); *qpair(2 * k + 1) = make_float2(v[k].z, v[k].w); }
 }
 
 // inclusive scan of affine maps x -> A x + B over the lanes of a warp (AR(1) recurrences)
@@ -271,9 +283,10 @@ __device__ __forceinline__ void issue_gemm(bool b_mn_major) {
 // update and the per-leaf bookkeeping that only needs this thread's own elements (see transition()).
 struct LeafTail {
   float hs;          // signed half step
-  const float* Lr;   // odd leaf: momentum of the previous (even) leaf = Left_0 of the level-0 merge (+ tid), else null
-  float* Fs;         // even leaf: FIRST[...] slot that receives this leaf's momentum (+ tid), else null
-  float* Es;         // leaf closing a level-1 left half: its e slot (+ tid; e at +VEC), else null
+  // (owner-layout float4 views of the calling thread, see own4())
+  const float4* Lr;  // odd leaf: momentum of the previous (even) leaf = Left_0 of the level-0 merge, else null
+  float4* Fs;        // even leaf: FIRST[...] slot that receives this leaf's momentum, else null
+  float4* Es;        // leaf closing a level-1 left half: its e slot, else null
   float kk, c1a, c1b;  // out: this thread's partial |P|^2 and the two level-0 U-turn dot products
 };
 
@@ -415,7 +428,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
 #pragma unroll 4
     for (int d = 0; d < 16; ++d) {
       const float2 v = *qpair(d);
-      const int s0 = m.map_i2s[(2 * d) * NT + tid], s1 = m.map_i2s[(2 * d + 1) * NT + tid];
+      const int s0 = m.map_i2s[oslot(2 * d, tid)], s1 = m.map_i2s[oslot(2 * d + 1, tid)];
       if (s0 >= 0) o[s0] = v.x;
       if (s1 >= 0) o[s1] = v.y;
     }
@@ -696,7 +709,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
   if (LEAF) {
     if (lt.Lr != nullptr) {
 #pragma unroll
-      for (int e = 0; e < EPT; ++e) lrv[e] = lt.Lr[e * NT];
+      for (int k = 0; k < 8; ++k) { const float4 t4 = lt.Lr[k * NT]; lrv[4 * k] = t4.x; lrv[4 * k + 1] = t4.y; lrv[4 * k + 2] = t4.z; lrv[4 * k + 3] = t4.w; }
     }
   }
   __syncthreads();  // S8
@@ -768,11 +781,12 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
         if (odd) ptx::tmem_st8f(tp + TM_G + 8 * c, lr);   // running sum of left rhos for the higher merges
         if (lt.Fs != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) lt.Fs[(c * 8 + j) * NT] = g[j];
+          for (int k = 0; k < 2; ++k) lt.Fs[(2 * c + k) * NT] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
         }
         if (lt.Es != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) lt.Es[VEC + (c * 8 + j) * NT] = g[j];   // (its r = b + e is re-formed by the level-1 merge)
+          for (int k = 0; k < 2; ++k)   // (its r = b + e is re-formed by the level-1 merge)
+            lt.Es[(2 * c + k) * NT] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
         }
       }
     }
@@ -808,13 +822,13 @@ __device__ __forceinline__ float block_sum_f(float v, int buf) {
 __device__ __forceinline__ float draw_momentum(const RunArgs& a, uint32_t tp, uint32_t chain_gid, uint32_t iter, uint32_t stream,
                                                uint32_t sub, uint32_t col) {
   float ss = 0.f;
-  const int32_t* map = a.m.map_i2s + threadIdx.x;
+  const int32_t* map = a.m.map_i2s;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     float v[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const int si = map[(h * 16 + j) * NT];
+      const int si = map[oslot(h * 16 + j, threadIdx.x)];
       v[j] = (si >= 0) ? rng_normal(a.seed, chain_gid, (uint32_t)si, iter, stream, sub) : 0.f;
       ss += v[j] * v[j];
     }
@@ -868,6 +882,7 @@ __device__ __forceinline__ void advance_q(uint32_t tp, float eps_signed) {
 __device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const float* Le, const float* Lr, const float* Rb, bool first,
                                             bool level1 = false) {
   const int tid = threadIdx.x;
+  const float4 *Lb4 = own4(Lb), *Le4 = own4(Le), *Lr4 = Lr ? own4(Lr) : nullptr, *Rb4 = Rb ? own4(Rb) : nullptr;
   float c1a = 0.f, c1b = 0.f, c2a = 0.f, c2b = 0.f, c3a = 0.f, c3b = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -881,19 +896,27 @@ __device__ __forceinline__ bool merge_check(uint32_t tp, const float* Lb, const 
     }
     ptx::tmem_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int gi = (h * 16 + j) * NT + tid;
-      const float lb = Lb[gi];
-      const float le = Le[gi];
-      const float lr = level1 ? le + lb : Lr[gi];
-      const float rb = level1 ? S[j] : ((Rb == nullptr) ? P[j] : Rb[gi]);
-      const float x = lr + S[j] + P[j];
-      c1a = fmaf(lb, x, c1a); c1b = fmaf(P[j], x, c1b);
-      const float y = lr + rb;
-      c2a = fmaf(lb, y, c2a); c2b = fmaf(rb, y, c2b);
-      const float z = S[j] + P[j] + le;
-      c3a = fmaf(le, z, c3a); c3b = fmaf(P[j], z, c3b);
-      S[j] += lr;
+    for (int k = 0; k < 4; ++k) {
+      const int gk = (4 * h + k) * NT;
+      const float4 lb4 = Lb4[gk], le4 = Le4[gk];
+      const float4 lr4 = level1 ? make_float4(0.f, 0.f, 0.f, 0.f) : Lr4[gk];
+      const float4 rb4 = (level1 || Rb == nullptr) ? make_float4(0.f, 0.f, 0.f, 0.f) : Rb4[gk];
+      const float lbv[4] = {lb4.x, lb4.y, lb4.z, lb4.w}, lev[4] = {le4.x, le4.y, le4.z, le4.w};
+      const float lrv[4] = {lr4.x, lr4.y, lr4.z, lr4.w}, rbv[4] = {rb4.x, rb4.y, rb4.z, rb4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 4 * k + i;
+        const float lb = lbv[i], le = lev[i];
+        const float lr = level1 ? le + lb : lrv[i];
+        const float rb = level1 ? S[j] : ((Rb == nullptr) ? P[j] : rbv[i]);
+        const float x = lr + S[j] + P[j];
+        c1a = fmaf(lb, x, c1a); c1b = fmaf(P[j], x, c1b);
+        const float y = lr + rb;
+        c2a = fmaf(lb, y, c2a); c2b = fmaf(rb, y, c2b);
+        const float z = S[j] + P[j] + le;
+        c3a = fmaf(le, z, c3a); c3b = fmaf(P[j], z, c3b);
+        S[j] += lr;
+      }
     }
     tm_st16(tp, TM_G + 16 * h, S);
   }
@@ -948,7 +971,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
   // the two trajectory ends, stored mid-leapfrog: (q +- eps s p_half, p_half), and the tree summary
   {
     const float hs = 0.5f * eps;
-    float* g = ws + tid;
+    float4* g4 = own4(ws);
+    constexpr int V4 = VEC / 4;   // float4s per slot
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       float P[16], s[16], gr[16];
@@ -957,22 +981,28 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       tm_ld16_nowait(tp, TM_G + 16 * h, gr);
       ptx::tmem_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float2 q0 = *qpair((h * 16 + j) >> 1);
+      for (int k = 0; k < 4; ++k) {
+        const float2 qa = *qpair(8 * h + 2 * k), qb = *qpair(8 * h + 2 * k + 1);
+        const float qq[4] = {qa.x, qa.y, qb.x, qb.y};
+        float pf[4], pb[4], qf[4], qbk[4];
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          const size_t gi = (size_t)(h * 16 + j + b) * NT;
-          const float qq = b ? q0.y : q0.x;
-          const float pf = fmaf(-hs * s[j + b], gr[j + b], P[j + b]), pb = fmaf(hs * s[j + b], gr[j + b], P[j + b]);
-          g[(size_t)SLOT_ENDF_P * VEC + gi] = pf;
-          g[(size_t)SLOT_ENDB_P * VEC + gi] = pb;
-          g[(size_t)SLOT_ENDF_Q * VEC + gi] = fmaf(eps * s[j + b], pf, qq);
-          g[(size_t)SLOT_ENDB_Q * VEC + gi] = fmaf(-eps * s[j + b], pb, qq);
-          g[(size_t)SLOT_TOP_BB * VEC + gi] = P[j + b];
-          g[(size_t)SLOT_TOP_FF * VEC + gi] = P[j + b];
-          g[(size_t)SLOT_TOP_RHO * VEC + gi] = P[j + b];
-          g[(size_t)SLOT_CAND_A * VEC + gi] = qq;
+        for (int i = 0; i < 4; ++i) {
+          const int j = 4 * k + i;
+          pf[i] = fmaf(-hs * s[j], gr[j], P[j]);
+          pb[i] = fmaf(hs * s[j], gr[j], P[j]);
+          qf[i] = fmaf(eps * s[j], pf[i], qq[i]);
+          qbk[i] = fmaf(-eps * s[j], pb[i], qq[i]);
         }
+        const int gk = (4 * h + k) * NT;
+        const float4 P4 = make_float4(P[4 * k], P[4 * k + 1], P[4 * k + 2], P[4 * k + 3]);
+        g4[SLOT_ENDF_P * V4 + gk] = make_float4(pf[0], pf[1], pf[2], pf[3]);
+        g4[SLOT_ENDB_P * V4 + gk] = make_float4(pb[0], pb[1], pb[2], pb[3]);
+        g4[SLOT_ENDF_Q * V4 + gk] = make_float4(qf[0], qf[1], qf[2], qf[3]);
+        g4[SLOT_ENDB_Q * V4 + gk] = make_float4(qbk[0], qbk[1], qbk[2], qbk[3]);
+        g4[SLOT_TOP_BB * V4 + gk] = P4;
+        g4[SLOT_TOP_FF * V4 + gk] = P4;
+        g4[SLOT_TOP_RHO * V4 + gk] = P4;
+        g4[SLOT_CAND_A * V4 + gk] = make_float4(qq[0], qq[1], qq[2], qq[3]);
       }
     }
   }
@@ -1034,9 +1064,9 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
 #endif
       LeafTail lt;
       lt.hs = hs;
-      lt.Lr = (t > 0) ? first_slot(n - 1) + tid : nullptr;
-      lt.Fs = (t == 0 && !last) ? first_slot(n) + tid : nullptr;
-      lt.Es = (t == 1 && !last) ? slot_ptr(ws, SLOT_LEFT) + tid : nullptr;
+      lt.Lr = (t > 0) ? own4((const float*)first_slot(n - 1)) : nullptr;
+      lt.Fs = (t == 0 && !last) ? own4(first_slot(n)) : nullptr;
+      lt.Es = (t == 1 && !last) ? own4(slot_ptr(ws, SLOT_LEFT) + VEC) : nullptr;
       eval_body<true>(none, lt);
       PROF_RESET;
       // one block reduction for |P|^2 and the two level-0 criteria (its barrier also publishes ctl.U)
@@ -1096,7 +1126,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       if (!last) {
         if (t >= 2) {
           // this subtree becomes the stored left half at level t: {e, r} (its b is FIRST[...]); t == 1 was stored above
-          float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1)) + tid;
+          float* Lt = slot_ptr(ws, SLOT_LEFT + 3 * (t - 1));
+          float4 *e4 = own4(Lt + VEC), *r4 = own4(Lt + 2 * VEC);
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
             float P[16], S[16];
@@ -1104,11 +1135,9 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
             tm_ld16_nowait(tp, TM_G + 16 * hh, S);
             ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int gi = (hh * 16 + j) * NT;
-              Lt[VEC + gi] = P[j];
-              Lt[2 * VEC + gi] = P[j] + S[j];
-            }
+            for (int j = 0; j < 16; ++j) S[j] += P[j];
+            st_groups4(e4, 4 * hh, P, 16);
+            st_groups4(r4, 4 * hh, S, 16);
           }
         }
       } else {
@@ -1118,8 +1147,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         const float* A = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB);
         const float* Rb = (depth == 0) ? nullptr : first_slot(0);
         persist = merge_check(tp, F, A, slot_ptr(ws, SLOT_TOP_RHO), Rb, depth == 0);
-        float* rho = slot_ptr(ws, SLOT_TOP_RHO) + tid;
-        float* endv = slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB) + tid;
+        float4* rho4 = own4(slot_ptr(ws, SLOT_TOP_RHO));
+        float4* end4 = own4(slot_ptr(ws, dir > 0 ? SLOT_TOP_FF : SLOT_TOP_BB));
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float P[16], S[16];
@@ -1127,11 +1156,9 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
           tm_ld16_nowait(tp, TM_G + 16 * hh, S);  // = old rho_top + sum of lower lefts
           ptx::tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int gi = (hh * 16 + j) * NT;
-            rho[gi] = S[j] + P[j];
-            endv[gi] = P[j];
-          }
+          for (int j = 0; j < 16; ++j) S[j] += P[j];
+          st_groups4(rho4, 4 * hh, S, 16);
+          st_groups4(end4, 4 * hh, P, 16);
         }
       }
       PROF(14);
@@ -1309,9 +1336,9 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
     const uint32_t gid = (uint32_t)(a.chain_id_offset + chain);
     float* qg = a.q + (size_t)chain * VEC;
     float* sg = a.sqrt_m + (size_t)chain * VEC;
-    float* wmean = a.wf_mean + (size_t)chain * VEC + tid;
-    float* wm2 = a.wf_m2 + (size_t)chain * VEC + tid;
-    const int32_t* map = a.m.map_i2s + tid;
+    float* wmean = a.wf_mean + (size_t)chain * VEC;   // owner layout: element e of this thread at oslot(e, tid)
+    float* wm2 = a.wf_m2 + (size_t)chain * VEC;
+    const int32_t* map = a.m.map_i2s;
     if (tid == 0) ctl.cs = a.cs[chain];
     __syncthreads();
 
@@ -1322,7 +1349,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
         for (int h = 0; h < 2; ++h) {
           float one[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) one[j] = (map[(h * 16 + j) * NT] >= 0) ? 1.0f : 0.f;
+          for (int j = 0; j < 16; ++j) one[j] = (map[oslot(h * 16 + j, tid)] >= 0) ? 1.0f : 0.f;
           tm_st16(tp, TM_S + 16 * h, one);
         }
         ptx::tmem_wait_st();
@@ -1333,7 +1360,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
 #pragma unroll 2
         for (int d = 0; d < 16; ++d) {
           float2 v = make_float2(0.f, 0.f);
-          const int s0 = map[(2 * d) * NT], s1 = map[(2 * d + 1) * NT];
+          const int s0 = map[oslot(2 * d, tid)], s1 = map[oslot(2 * d + 1, tid)];
           uint32_t rw[4];
           if (s0 >= 0) { rng_words(a.seed, gid, (uint32_t)s0, 0, 0, attempt, rw); v.x = a.init_radius * (2.0f * u01(rw[0]) - 1.0f); }
           if (s1 >= 0) { rng_words(a.seed, gid, (uint32_t)s1, 0, 0, attempt, rw); v.y = a.init_radius * (2.0f * u01(rw[0]) - 1.0f); }
@@ -1362,7 +1389,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
         cs.iter = 0; cs.n_leapfrog = 0;
       }
 #pragma unroll 8
-      for (int e = 0; e < EPT; ++e) { wmean[e * NT] = 0.f; wm2[e * NT] = 0.f; }
+      for (int e = 0; e < EPT; ++e) { wmean[oslot(e, tid)] = 0.f; wm2[oslot(e, tid)] = 0.f; }
       __syncthreads();
       const float e0 = find_stepsize(a, ws, gid, 0xFFFFFFFFu, 1.0f);
       if (tid == 0) { ctl.cs.eps = e0; ctl.cs.da_mu = log(10.0 * (double)e0); }
@@ -1420,7 +1447,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
             const float2 q = *qpair(d);
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
-              const int gi = (2 * d + b) * NT;
+              const int gi = oslot(2 * d + b, tid);
               const float qq = b ? q.y : q.x;
               const float mu = wmean[gi], dd = qq - mu, mu2 = fmaf(dd, inv, mu);
               wmean[gi] = mu2;
@@ -1436,7 +1463,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
             float s[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const int gi = (h * 16 + j) * NT;
+              const int gi = oslot(h * 16 + j, tid);
               float v = 0.f;
               if (map[gi] >= 0) {
                 const float var = wm2[gi] / (n - 1.0f);

@@ -88,6 +88,10 @@ __host__ __device__ inline int nz_slot(int w, int ln, int e) {
   return w * (NZ_LANES * EPT) + ((15 - (e >> 1)) * NZ_LANES + ln) * 2 + (e & 1);
 }
 
+// owner layout of a D-vector in global memory: element e (0..31) of thread tid lives at ((e/4)*NT + tid)*4 + e%4, i.e.
+// every thread moves its elements as eight float4s and a warp's accesses are 512 contiguous bytes.
+__host__ __device__ inline int oslot(int e, int tid) { return ((e >> 2) * NT + tid) * 4 + (e & 3); }
+
 // ---- packed poll index: s[0:6) d[6:14) p[14:24) m[24:27) o[27:30) unadj[30]
 __host__ __device__ inline uint32_t pack_poll(int s, int d, int p, int m, int o, int un) {
   return (uint32_t)s | ((uint32_t)d << 6) | ((uint32_t)p << 14) | ((uint32_t)m << 24) | ((uint32_t)o << 27) |
