@@ -357,6 +357,7 @@ int build_model(const PotusData* d, HostModel& hm) {
 
   // ---- owner-layout map: internal slot -> Stan unconstrained index
   hm.map_i2s.assign(VEC, -1);
+  m.urho_owner = -1;
   for (int tid = 0; tid < NT; ++tid) {
     int wq = tid >> 5, l = tid & 31;
     for (int e = 0; e < EPT; ++e) {
@@ -366,6 +367,7 @@ int build_model(const PotusData* d, HostModel& hm) {
         if (s < S && t < T) idx = o.Z + s + S * t;
       } else {
         int k = nz_slot(wq, l - ZLANES, e);
+        if (full && k == m.nz_urho) m.urho_owner = tid;
         if (k < m.NZ) {
           if (k < m.nz_c) idx = o.zT + (k - m.nz_zT);
           else if (k < m.nz_c + P) idx = o.c + (k - m.nz_c);
@@ -381,6 +383,7 @@ int build_model(const PotusData* d, HostModel& hm) {
       hm.map_i2s[oslot(e, tid)] = idx;
     }
   }
+  if (full && m.urho_owner < 0) return fail(POTUS_ERR_STATE, "rho_e_bias has no owner thread");
   {  // every Stan index must be covered exactly once
     std::vector<int> cnt(o.D, 0);
     for (int v : hm.map_i2s) if (v >= 0) { if (v >= o.D) return fail(POTUS_ERR_STATE, "internal map out of range"); cnt[v]++; }

@@ -322,7 +322,10 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
       const float2 v = *reinterpret_cast<const float2*>(qn - d * (2 * NZ_LANES));
       qsq = fmaf(v.x, v.x, fmaf(v.y, v.y, qsq));
     }
-    if (m.full && tid == ZLANES) { const float v = sQNZ()[m.nz_urho]; qsq -= v * v; }  // rho's unconstrained value carries no N(0,1) term
+    // rho's unconstrained value carries no N(0,1) term.  Only the OWNER of that slot may read it here: we are before
+    // barrier S1 and the owner updated it in advance_q with no barrier since (any other reader races; seen by racecheck
+    // and as a run-to-run flake, profiles/r01_d_racecheck_fused_kernel.log)
+    if (tid == m.urho_owner) { const float v = sQNZ()[m.nz_urho]; qsq -= v * v; }
   }
   __syncthreads();  // S1
   PROF(0);
@@ -1110,8 +1113,8 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
         }
       }
       PROF(12);
-      // position update q' = q + eps*s*p_half' (after the candidate copy above; each thread touches only its own
-      // elements, and the first cross-thread read of q comes after barrier S1 of the next gradient)
+      // position update q' = q + eps*s*p_half' (after the candidate copy above).  No barrier follows: this is safe only
+      // because, until barrier S1 of the next gradient, every thread reads nothing of q but the elements it owns
       advance_q(tp, eps_s);
       PROF(15);
       // U-turn checks for every subtree this leaf completes (level 0 came with the reduction above)

@@ -108,6 +108,7 @@ struct ModelDev {
   int S, T, P, M, Pop, Nn, Ns, N, full, D, NZ, npair;
   int nz_zT, nz_c, nz_m, nz_pop, nz_umu, nz_urho, nz_ze, nz_x, nz_zb;  // offsets inside the nz block
   int n_t1, n_t2, n_cell, n_ids;
+  int urho_owner;           // thread that owns the nz slot of rho_e_bias (-1 if the model has none); see eval_body P1
   float a_b, a_T, a_w, sig_c, sig_m, sig_pop, sig_n, sig_s, sig_e;
   float scale_G, inv_scale_G;
   double lp_const;          // sum_i y_i*eta_hat_i - n_i*softplus(eta_hat_i): the centring constant
