@@ -35,8 +35,8 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_LEAPFROG = 4 * 15098 * 4          # read q,p + write q,p once, fp32 state (2016: 241 568 B)
 ALGO_FLOPS_PER_LEAPFROG = 4 * 51 * 51 * 254 + 20 * 1619 + 10 * 15098
 # dram__bytes_read.sum + dram__bytes_write.sum of potus_nuts_kernel from the ncu --set full capture in
-# profiles/r01_c_final_kernel.txt (26.146 GB over 286 391 leapfrogs): NUTS tree checkpoints, the state itself is on chip
-NCU_DRAM_BYTES_PER_LEAPFROG = 26.146e9 / 286391
+# profiles/r01_e_final_kernel.txt (26.146 GB over 286 391 leapfrogs): NUTS tree checkpoints, the state itself is on chip
+NCU_DRAM_BYTES_PER_LEAPFROG = 25.435008e9 / 286391
 
 
 def load_peaks():
@@ -309,7 +309,7 @@ def main():
         "roofline": {"bound": "hbm", "achieved": per_gpu_rate * ALGO_BYTES_PER_LEAPFROG / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": per_gpu_rate * ALGO_BYTES_PER_LEAPFROG / 1e9 / peak,
                      "traffic": NCU_DRAM_BYTES_PER_LEAPFROG * (lf_samp / max(args.steps, 1) / world),
-                     "traffic_note": "bytes per sampling-phase launch = ncu DRAM bytes per leapfrog (profiles/r01_c_final_kernel.txt) x leapfrogs in the launch; algorithmic bytes per launch = 241568 x leapfrogs",
+                     "traffic_note": "bytes per sampling-phase launch = ncu DRAM bytes per leapfrog (profiles/r01_e_final_kernel.txt) x leapfrogs in the launch; algorithmic bytes per launch = 241568 x leapfrogs",
                      "kernel": "potus_nuts_kernel (sampling-phase launch)", "peak_source": peak_src,
                      "algorithmic_bytes_per_leapfrog": ALGO_BYTES_PER_LEAPFROG,
                      "tensor_frac_of_bf16_peak": per_gpu_rate * 4 * 51 * 51 * 254 / 1700.3e12},
