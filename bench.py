@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_LEAPFROG = 4 * 15098 * 4          # read q,p + write q,p once, fp32 state (2016: 241 568 B)
 ALGO_FLOPS_PER_LEAPFROG = 4 * 51 * 51 * 254 + 20 * 1619 + 10 * 15098
 # dram__bytes_read.sum + dram__bytes_write.sum of potus_nuts_kernel from the ncu --set full capture in
-# profiles/r01_e_final_kernel.txt (26.146 GB over 286 391 leapfrogs): NUTS tree checkpoints, the state itself is on chip
+# profiles/r01_e_final_kernel.txt (25.435 GB over 286 391 leapfrogs): NUTS tree checkpoints, the state itself is on chip
 NCU_DRAM_BYTES_PER_LEAPFROG = 25.435008e9 / 286391
 
 
