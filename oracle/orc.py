@@ -49,7 +49,7 @@ def lib():
         L.orc_logp_grad.restype = C.c_double
         L.orc_constrain.argtypes = [C.c_void_p] + [f64p] * 7
         L.orc_sample.argtypes = [C.c_void_p, C.POINTER(cabi.PotusConfig), C.c_int, C.c_int, C.c_int, C.c_int, f64p, f64p, f64p,
-                                 f64p, i64p]
+                                 f64p, i64p, f64p]
         L.orc_sample.restype = C.c_double
         L.orc_transitions.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, f64p, f64p, C.c_uint32,
                                       C.c_int, f64p, f64p]
@@ -98,7 +98,7 @@ class OracleModel:
         return out
 
     def sample(self, chains=4, iter_warmup=500, iter_sampling=500, seed=1843, threads=None, literal=False, tree_mode=0,
-               max_iters=0, save_theta=False, chain_id_offset=0, max_treedepth=10, adapt_delta=0.8):
+               max_iters=0, save_theta=False, chain_id_offset=0, max_treedepth=10, adapt_delta=0.8, save_inv_metric=False):
         cfg = cabi.make_config(chains=chains, iter_warmup=iter_warmup, iter_sampling=iter_sampling, seed=seed,
                                chain_id_offset=chain_id_offset, max_treedepth=max_treedepth, adapt_delta=adapt_delta)
         threads = threads or min(chains, os.cpu_count() or 1)
@@ -107,10 +107,11 @@ class OracleModel:
         stats = np.full((chains, iter_warmup + iter_sampling, 7), np.nan)
         eps = np.zeros(chains)
         nlf = np.zeros(chains, dtype=np.int64)
+        im = np.zeros((chains, self.D)) if save_inv_metric else None
         secs = lib().orc_sample(self.h, C.byref(cfg), int(literal), int(tree_mode), int(threads), int(max_iters),
                                 _p(theta) if save_theta else None, _p(mon), _p(stats), _p(eps),
-                                nlf.ctypes.data_as(C.POINTER(C.c_int64)))
-        return dict(theta=theta, monitor=mon, stats=stats, stepsize=eps, n_leapfrog=nlf, seconds=secs, threads=threads)
+                                nlf.ctypes.data_as(C.POINTER(C.c_int64)), _p(im) if save_inv_metric else None)
+        return dict(inv_metric=im, theta=theta, monitor=mon, stats=stats, stepsize=eps, n_leapfrog=nlf, seconds=secs, threads=threads)
 
     def transitions(self, q0, eps, inv_metric, n_iter=1, seed=1843, chain=0, tree_mode=1, max_depth=10, iter0=0):
         q0 = np.ascontiguousarray(q0, dtype=np.float64)

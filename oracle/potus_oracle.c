@@ -558,6 +558,7 @@ static void adapt_init(Adapt* a, int D, int num_warmup, double delta) {
     a->base_window = num_warmup - (a->init_buffer + a->term_buffer);
   }
   a->window_size = a->base_window; a->next_window = a->init_buffer + a->window_size - 1;
+  if (num_warmup < 20) a->next_window = -1; /* Stan: adapt_next_window_ stays UINT_MAX, no window ever ends */
   a->mean = (double*)calloc(D, sizeof(double)); a->m2 = (double*)calloc(D, sizeof(double));
 }
 static void learn_stepsize(Adapt* a, double* eps, double adapt_stat) {
@@ -610,6 +611,7 @@ typedef struct OrcRun {
   int64_t* n_leapfrog; /* [chains] total */
   int next_chain; pthread_mutex_t mu;
   int max_iters;       /* optional cap on transitions per chain (bounded benchmarks); <=0: none */
+  double* inv_metric_out; /* optional [chains][D]: the adapted diagonal of M^-1 at the end of the run */
 } OrcRun;
 
 static void run_chain(OrcRun* r, int ci) {
@@ -662,6 +664,7 @@ static void run_chain(OrcRun* r, int ci) {
     }
   }
   r->final_eps[ci] = c.eps; r->n_leapfrog[ci] = total_lf;
+  if (r->inv_metric_out) memcpy(r->inv_metric_out + (size_t)ci * D, c.inv_metric, sizeof(double) * D);
   free(a.mean); free(a.m2); free(c.inv_metric); free(c.q); free(c.p); free(c.g); free(c.arena); work_free(c.wk);
 }
 static void* worker(void* arg) {
@@ -679,10 +682,11 @@ static void* worker(void* arg) {
 /* Run `cfg->chains` chains of Stan-semantics NUTS on n_threads host threads (one chain per thread
  * at a time).  Outputs are caller-allocated; theta_out may be NULL.  Returns wall seconds. */
 ORC_API double orc_sample(const OrcModel* m, const PotusConfig* cfg, int literal, int tree_mode, int n_threads, int max_iters,
-                          double* theta_out, double* monitor, double* stats, double* final_eps, int64_t* n_leapfrog) {
+                          double* theta_out, double* monitor, double* stats, double* final_eps, int64_t* n_leapfrog,
+                          double* inv_metric_out) {
   OrcRun r; memset(&r, 0, sizeof(r));
   r.m = m; r.cfg = *cfg; r.literal = literal; r.tree_mode = tree_mode; r.n_threads = n_threads; r.max_iters = max_iters;
-  r.theta_out = theta_out; r.monitor = monitor; r.stats = stats; r.final_eps = final_eps; r.n_leapfrog = n_leapfrog;
+  r.inv_metric_out = inv_metric_out; r.theta_out = theta_out; r.monitor = monitor; r.stats = stats; r.final_eps = final_eps; r.n_leapfrog = n_leapfrog;
   pthread_mutex_init(&r.mu, NULL);
   struct timespec t0, t1; clock_gettime(CLOCK_MONOTONIC, &t0);
   if (n_threads < 1) n_threads = 1;

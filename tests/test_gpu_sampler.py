@@ -144,6 +144,14 @@ def test_posterior_matches_reference_tables_2016(pkg, datalists, cuda_lib):
     ora = json.load(open(os.path.join(GOLDEN, "oracle_posterior_2016.json")))
     z = np.abs(mean - np.array(ora["mean"])) / (4 * np.array(ora["mcse"]) + 5e-4)
     assert z.max() <= 1.0, z.max()
+    # the north_star's 90% intervals (5% / 95%; the README prints 2.5 / 97.5 only): device vs the long fp64 oracle run.
+    # Tolerance: Monte-Carlo error of a tail quantile ~ 2.1 x MCSE of the mean (density at the 5% point of a normal),
+    # so 4 x 2.1 x mcse + 1e-3 for the oracle's own 4000-draw quantile error
+    q05, q95 = np.quantile(p, 0.05, axis=0), np.quantile(p, 0.95, axis=0)
+    tolq = 8.4 * np.array(ora["mcse"]) + 1e-3
+    dq = max(np.abs(q05 - np.array(ora["q05"])).max(), np.abs(q95 - np.array(ora["q95"])).max())
+    print(f"2016 90% interval ends vs oracle: max|d| {dq:.4f}")
+    assert np.all(np.abs(q05 - np.array(ora["q05"])) <= tolq) and np.all(np.abs(q95 - np.array(ora["q95"])) <= tolq)
     ess = pkg.diagnostics.ess(p[:, 9].reshape(296, 200))
     assert ess > 0.2 * p.shape[0]
     # the reports' headline numbers (README.md:260): Brier scores and states called, from OUR draws
@@ -190,6 +198,9 @@ def test_posterior_matches_reference_tables_2012_no_mode(pkg, datalists, cuda_li
     ora = json.load(open(os.path.join(GOLDEN, "oracle_posterior_2012.json")))
     z = np.abs(mean - np.array(ora["mean"])) / (4 * np.array(ora["mcse"]) + 5e-4)
     assert z.max() <= 1.0, z.max()
+    q05, q95 = np.quantile(p, 0.05, axis=0), np.quantile(p, 0.95, axis=0)   # 90% interval, as in the 2016 test
+    tolq = 8.4 * np.array(ora["mcse"]) + 1.5e-3                                # (148 x 200 device draws here)
+    assert np.all(np.abs(q05 - np.array(ora["q05"])) <= tolq) and np.all(np.abs(q95 - np.array(ora["q95"])) <= tolq)
 
 
 def test_same_seed_same_binary_is_bit_reproducible(pkg, datalists, cuda_lib):
@@ -206,3 +217,90 @@ def test_same_seed_same_binary_is_bit_reproducible(pkg, datalists, cuda_lib):
     for r in runs[1:]:
         for k in runs[0]:
             assert np.array_equal(runs[0][k], r[k]), f"{k} differs between identical runs"
+
+
+@pytest.mark.parametrize("year", [2012, 2008])
+def test_no_mode_draw_record_offsets(pkg, orc_mod, datalists, cuda_lib, year, tmp_path):
+    """The no-mode data lists still carry M and Pop (final_2012.R:501-540, final_2008.R:504-545) although the model has no
+    mu_m / mu_pop blocks.  The draw record must be read where the kernel wrote it: polling_bias, mu_c and theta of the
+    2012/2008 fits against the oracle's constrain() at the same theta (polling_bias is extracted at final_2012.R:623,
+    final_2008.R:627), and the CmdStan CSV of the no-mode variant round-trips."""
+    d = datalists[year]
+    assert int(d["M"]) >= 1 and int(d["Pop"]) >= 1 and "poll_mode_state" not in d
+    fit = pkg.cmdstan_model("poll_model_2020_no_mode_adjustment.stan").sample(data=d, seed=11, chains=3, iter_warmup=25,
+                                                                              iter_sampling=4, keep_per_chain=2)
+    ex = fit.extract(["mu_b", "mu_c", "polling_bias"])
+    th = fit.theta()
+    om = orc_mod.OracleModel(d)
+    assert th.shape == (6, om.D) and np.all(np.isfinite(th)) and np.abs(th).max() < 50
+    for k in range(6):
+        c = om.constrain(th[k])
+        assert np.abs(c["mu_b"] - ex["mu_b"][k]).max() < 2e-5
+        assert np.abs(c["mu_c"] - ex["mu_c"][k]).max() < 1e-6
+        assert np.abs(c["polling_bias"] - ex["polling_bias"][k]).max() < 1e-5
+    sp = fit.sampler_params()
+    lp_o = np.array([om.logp_grad(th[k])[0] for k in range(6)])
+    assert np.abs(sp["lp__"][:, 25:][:, 1::2].reshape(-1) - lp_o).max() < 0.05
+    paths = fit.save_csvfiles(str(tmp_path))
+    back = pkg.stancsv.read_stan_csv(paths)
+    for c in range(3):
+        for k in range(2):
+            assert np.allclose(back["draws"]["polling_bias"][k, c], ex["polling_bias"][2 * c + k], rtol=1e-5, atol=1e-6)
+            assert np.allclose(back["draws"]["raw_polling_bias"][k, c], th[2 * c + k, -51:], rtol=1e-5, atol=1e-6)
+
+
+def test_no_metric_adaptation_below_20_warmup_iterations_on_device(pkg, orc_mod, datalists, cuda_lib):
+    """iter_warmup < 20: Stan performs no variance adaptation; the inverse metric stays 1 and sampling runs at exp(x_bar)
+    of one uninterrupted dual-averaging run.  (The kernel used to fire a window end on the last warm-up iteration with zero
+    samples: metric 1e-3, step size 1.)  Decision-level agreement with the oracle through warm-up AND the first sampling
+    iterations pins the hand-over."""
+    d = datalists[2016]
+    fit = pkg.cmdstan_model().sample(data=d, seed=1843, chains=2, iter_warmup=12, iter_sampling=3, keep_per_chain=1)
+    assert np.all(fit.inv_metric() == 1.0)
+    sp = fit.sampler_params()
+    r = orc_mod.OracleModel(d).sample(chains=2, iter_warmup=12, iter_sampling=3, seed=1843, threads=2, tree_mode=1)
+    for c in range(2):
+        assert np.all(sp["stepsize__"][c, 12:] == sp["stepsize__"][c, 12])
+        assert abs(sp["stepsize__"][c, 12] / r["stepsize"][c] - 1) < 0.02
+        assert np.array_equal(sp["treedepth__"][c, :12], r["stats"][c, :12, 3])
+
+
+def test_adaptation_matches_oracle_distribution(pkg, datalists, cuda_lib):
+    """SURVEY 8(a) row a12 against the oracle, past the first window: 296 device chains x 500 warm-up iterations vs the
+    committed 64-chain fp64 oracle run (tests/golden/oracle_adaptation_2016.npz, make_oracle_adaptation.py; independent
+    chain ids, same law).  (i) per-coordinate mean over chains of log(inverse metric): |device - oracle| within 4 standard
+    errors of the difference (+1% slack), for every one of the 15098 coordinates; (ii) the final step size: means within
+    4 SE, spread within a factor 1.5; (iii) the step size restarts exactly after the window ends 99/149/249/449 (Stan
+    defaults 75/25/50): it moves by > 8% there in (almost) every chain -- init_stepsize + the reset of dual averaging --
+    and nowhere else late in a window; (iv) frozen after warm-up."""
+    d = datalists[2016]
+    ora = np.load(os.path.join(GOLDEN, "oracle_adaptation_2016.npz"))
+    C = 296
+    fit = pkg.cmdstan_model().sample(data=d, seed=1843, chains=C, iter_warmup=500, iter_sampling=4, keep_per_chain=1)
+    im = fit.inv_metric()
+    lm, ls = np.log(im).mean(0), np.log(im).std(0, ddof=1)
+    n_o = int(ora["chains"])
+    se = np.sqrt(ls ** 2 / C + ora["log_inv_metric_sd"].astype(np.float64) ** 2 / n_o)
+    z = np.abs(lm - ora["log_inv_metric_mean"]) / (4 * se + 0.01)
+    print(f"a12: log inv-metric max z {z.max():.3f} (coordinate {int(z.argmax())}); median ratio {np.exp(np.median(lm - ora['log_inv_metric_mean'])):.4f}")
+    assert z.max() <= 1.0, (z.max(), int(z.argmax()))
+    sp = fit.sampler_params()
+    eps_f = sp["stepsize__"][:, 500]
+    eo = ora["stepsize"]
+    se_e = np.sqrt(eps_f.var(ddof=1) / C + eo.var(ddof=1) / n_o)
+    print(f"a12: final eps device {eps_f.mean():.5f} +- {eps_f.std(ddof=1):.5f}, oracle {eo.mean():.5f} +- {eo.std(ddof=1):.5f}")
+    assert abs(eps_f.mean() - eo.mean()) <= 4 * se_e + 1e-4
+    assert 1 / 1.5 < eps_f.std(ddof=1) / eo.std(ddof=1) < 1.5
+    eps = sp["stepsize__"][:, :500]
+    jump = np.abs(np.log(eps[:, 1:] / eps[:, :-1]))       # jump[:, k]: iteration k -> k+1
+    # after a window end the step size is re-initialised and dual averaging restarts from mu = log(10 eps): the FIRST
+    # learn_stepsize of the new run moves eps by a factor 10*exp(-(0.8-a)/(11*0.05)) in [2.3, 14] -- at wend+1 -> wend+2,
+    # in every chain, and (restart = counter reset) nowhere else is a move that large systematic
+    for wend in (99, 149, 249, 449):
+        assert (jump[:, wend + 1] > 0.7).mean() > 0.97, (wend, (jump[:, wend + 1] > 0.7).mean())
+    other = np.ones(499, bool); other[[100, 150, 250, 450]] = False; other[:100] = False
+    assert (jump[:, other] > 0.7).mean() < 0.01
+    assert np.all(sp["stepsize__"][:, 500:] == sp["stepsize__"][:, 500:501])
+    by_iter = np.abs(np.log(eps.mean(0)[100:] / ora["stepsize_by_iter"][100:500]))   # the whole adaptation path, not just its end:
+    print(f"a12: mean step size by iteration vs oracle: median |log ratio| {np.median(by_iter):.3f}, max {by_iter.max():.3f}")
+    assert np.median(by_iter) < 0.06 and by_iter.max() < 0.3     # per-iteration eps has ~30% spread; oracle mean is over 64 chains

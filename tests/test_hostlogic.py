@@ -214,3 +214,17 @@ def test_stan_csv_layout_and_roundtrip(pkg, datalists, year, tmp_path):
         rho = po.sigmoid(par["rho_e_bias"][0])
         prior += -0.5 * ((rho - 0.7) / 0.1) ** 2 + np.log(rho * (1 - rho))
     assert abs((ll + prior) - lp) < 1e-6 * abs(lp)
+
+
+def test_short_or_long_vectors_are_rejected_before_the_library_sees_them(datalists):
+    """marshal_data checks every vector length against N_state_polls / N_national_polls / S (Stan: "mismatch in dimension
+    declared and found in context"); without it validate() would index past the end of a short vector."""
+    from us_potus_model_b200 import cabi
+    base = datalists[2016]
+    for key in ("state", "n_two_share_national", "unadjusted_state", "mu_b_prior"):
+        d = dict(base); d[key] = np.asarray(base[key])[:-1]
+        with pytest.raises(ValueError, match="mismatch in dimension.*" + key):
+            cabi.marshal_data(d)
+    d = dict(base); d["state_covariance_0"] = np.asarray(base["state_covariance_0"])[:50, :50]
+    with pytest.raises(ValueError, match="state_covariance_0"):
+        cabi.marshal_data(d)

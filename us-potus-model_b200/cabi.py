@@ -81,6 +81,15 @@ def marshal_data(data: dict):
             raise KeyError(f"data list is missing '{k}'")
         setattr(pd, k, float(v))
     full = "poll_mode_state" in data
+
+    def _expect_len(name: str, arr) -> None:
+        # Stan's own message shape for a short/long vector ("mismatch in dimension declared and found in context")
+        want = pd.N_state_polls if name.endswith("_state") or name == "state" else (
+            pd.N_national_polls if name.endswith("_national") else pd.S)
+        if arr.ndim != 1 or arr.shape[0] != want:
+            raise ValueError(f"Exception: mismatch in dimension declared and found in context; processing stage=data initialization; "
+                             f"variable name={name}; position=0; dims declared=({want}); dims found=({','.join(map(str, arr.shape))})")
+
     for k in _INT_VECS:
         if k not in data:
             if k.startswith("poll_mode") or k.startswith("poll_pop"):
@@ -92,6 +101,7 @@ def marshal_data(data: dict):
             if not np.all(a == np.rint(a)):
                 raise ValueError(f"{k} must hold integers")
         arr = np.ascontiguousarray(a, dtype=np.int32)
+        _expect_len(k, arr)
         keep.append(arr)
         setattr(pd, k, arr.ctypes.data_as(_i32p))
     for k in _DBL_VECS:
@@ -101,9 +111,13 @@ def marshal_data(data: dict):
                 continue
             raise KeyError(f"data list is missing '{k}'")
         arr = np.ascontiguousarray(np.asarray(data[k], dtype=np.float64))
+        _expect_len(k, arr)
         keep.append(arr)
         setattr(pd, k, arr.ctypes.data_as(_f64p))
     cov = np.asarray(data["state_covariance_0"], dtype=np.float64)
+    if cov.shape != (pd.S, pd.S):
+        raise ValueError(f"Exception: mismatch in dimension declared and found in context; processing stage=data initialization; "
+                         f"variable name=state_covariance_0; position=0; dims declared=({pd.S},{pd.S}); dims found=({','.join(map(str, cov.shape))})")
     cov = np.asfortranarray(cov)
     flat = np.ascontiguousarray(cov.reshape(-1, order="F"))
     keep.append(flat)

@@ -158,7 +158,9 @@ int build_model(const PotusData* d, HostModel& hm) {
   const int S = d->S, T = d->T, P = d->P, Ns = d->N_state_polls, Nn = d->N_national_polls, N = Ns + Nn;
   const bool full = d->poll_mode_state != nullptr;
   const int M = full ? d->M : 0, Pop = full ? d->Pop : 0;
-  hm.S = S; hm.T = T; hm.P = P; hm.M = d->M; hm.Pop = d->Pop; hm.Ns = Ns; hm.Nn = Nn; hm.N = N; hm.full = full;
+  // (the no-mode model has no mu_m / mu_pop blocks although its data list still carries M and Pop:
+  //  the draw record the kernel writes uses M = Pop = 0 there, and so must every host-side offset)
+  hm.S = S; hm.T = T; hm.P = P; hm.M = M; hm.Pop = Pop; hm.Ns = Ns; hm.Nn = Nn; hm.N = N; hm.full = full;
   // Stan unconstrained order (poll_model_2020.stan:56-69)
   Offsets& o = hm.o;
   int off = 0;
@@ -516,7 +518,7 @@ static RunArgs make_args(PotusSampler* s, int it0, int it1, int do_init) {
   int nw = s->cfg.iter_warmup, ib = 75, tb = 50, bw = 25;
   if (nw < 20) { ib = nw; tb = 0; bw = 0; }
   else if (ib + bw + tb > nw) { ib = (int)(0.15 * nw); tb = (int)(0.1 * nw); bw = nw - (ib + tb); }
-  a.w_init_buffer = ib; a.w_term_buffer = tb; a.w_base_window = bw;
+  a.w_init_buffer = ib; a.w_term_buffer = tb; a.w_base_window = bw;   // bw == 0 (nw < 20): no window ever ends, see the kernel's do_init block
   a.seed = s->cfg.seed; a.adapt_delta = (float)s->cfg.adapt_delta; a.init_radius = (float)s->cfg.init_radius;
   a.q = s->q; a.sqrt_m = s->sqrt_m; a.wf_mean = s->wf_mean; a.wf_m2 = s->wf_m2; a.cs = s->cs; a.workspace = s->workspace;
   a.queue = s->queue; a.draws = s->draws; a.monitor = s->monitor; a.sampler_params = s->sparams;

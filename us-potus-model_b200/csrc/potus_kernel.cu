@@ -1388,7 +1388,9 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
         ChainState& cs = ctl.cs;
         cs.status = good ? 0 : -1;
         cs.eps = 1.0f; cs.da_counter = 0; cs.da_sbar = 0; cs.da_xbar = 0;
-        cs.w_counter = 0; cs.w_size = a.w_base_window; cs.w_next = a.w_init_buffer + a.w_base_window - 1; cs.w_nsamp = 0;
+        cs.w_counter = 0; cs.w_size = a.w_base_window; cs.w_nsamp = 0;
+        // Stan's windowed_adaptation leaves adapt_next_window_ at UINT_MAX for num_warmup < 20: no metric update at all
+        cs.w_next = a.w_base_window > 0 ? a.w_init_buffer + a.w_base_window - 1 : -1;
         cs.iter = 0; cs.n_leapfrog = 0;
       }
 #pragma unroll 8
