@@ -33,7 +33,7 @@ extern "C" {
 
 #define POTUS_OK 0
 #define POTUS_ERR_INVALID_DATA (-1)   /* Stan data-block constraint violated (poll_model_2020.stan:9-23,37) */
-#define POTUS_ERR_UNSUPPORTED (-2)    /* problem size outside what the resident kernel handles */
+#define POTUS_ERR_UNSUPPORTED (-2)    /* problem size outside both kernel families (resident: S<=51,T<=254,N<=1648; streaming: S<=256,T<=512) */
 #define POTUS_ERR_CUDA (-3)           /* CUDA runtime / driver error, or no sm_100 device */
 #define POTUS_ERR_STATE (-4)          /* call order (e.g. get_draws before run) or unknown name */
 #define POTUS_ERR_INIT (-5)           /* no finite initial point after 100 attempts (Stan's rule) */
@@ -79,11 +79,14 @@ typedef struct PotusConfig {
                            /* 7 sampler diagnostics are always kept for every iteration.           */
   int32_t max_treedepth;   /* default 10 */
   int32_t device;          /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t flags;           /* bit 0 (POTUS_FLAG_FORCE_STREAM): run the streaming large-S/T kernel family even when    */
+                           /* the problem fits the SMEM/TMEM-resident kernel (used by the parity tests)            */
   uint64_t seed;           /* default 1843 (final_2016.R:535) */
   double adapt_delta;      /* default 0.8 */
   double init_radius;      /* default 2.0: inits ~ U(-r, r) on the unconstrained scale */
 } PotusConfig;
+
+#define POTUS_FLAG_FORCE_STREAM 1
 
 typedef struct PotusStats {
   int64_t n_leapfrog_total;      /* all chains, warm-up + sampling                           */
@@ -134,6 +137,8 @@ POTUS_API const char* potus_last_error(void);
  * excluded) and gradient for n_chains unconstrained vectors theta[n_chains][D] (Stan order),
  * evaluated by the same device code the sampler uses. */
 POTUS_API int potus_logp_grad(const PotusData* data, const double* theta, int n_chains, double* lp, double* grad);
+/* Same, with force_stream != 0 evaluating on the streaming kernel family (BASELINE config 5 path) whatever the size. */
+POTUS_API int potus_logp_grad_ex(const PotusData* data, const double* theta, int n_chains, double* lp, double* grad, int force_stream);
 /* Unconstrained dimension for a data list (15098 for the 2016 list). */
 POTUS_API int potus_num_params(const PotusData* data);
 

@@ -18,7 +18,7 @@ def _declared_functions():
 def test_library_exports_every_declared_symbol(cuda_lib):
     from us_potus_model_b200 import cabi
     names = _declared_functions()
-    assert len(names) == 10 and set(names) == set(cabi.EXPORTS)
+    assert len(names) == len(cabi.EXPORTS) >= 11 and set(names) == set(cabi.EXPORTS)
     for n in names:
         assert getattr(cuda_lib, n) is not None
 
@@ -85,7 +85,10 @@ def test_invalid_data_is_rejected_like_stan(cuda_lib, datalists):
     assert rc == -1
     d = dict(base); d["n_democrat_state"] = base["n_democrat_state"].copy(); d["n_democrat_state"][0] = 10 ** 6
     assert create(d)[0] == -1
-    # sizes the resident kernel does not hold are refused with POTUS_ERR_UNSUPPORTED, not silently mangled
-    big = __import__("potus_pkg").load().synthetic_datalist(S=60, T=100, N_state=500, N_national=100, P=20)
+    # sizes neither kernel family holds are refused with POTUS_ERR_UNSUPPORTED, not silently mangled
+    # (S=60 is beyond the resident kernel and is routed to the streaming family: tests/test_gpu_stream.py)
+    big = __import__("potus_pkg").load().synthetic_datalist(S=300, T=100, N_state=500, N_national=100, P=20)
     rc, msg = create(big)
-    assert rc == -2 and "outside the resident kernel" in msg
+    assert rc == -2 and "outside the streaming kernel" in msg
+    big = __import__("potus_pkg").load().synthetic_datalist(S=60, T=600, N_state=500, N_national=100, P=20)
+    assert create(big)[0] == -2

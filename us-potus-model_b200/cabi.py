@@ -37,7 +37,7 @@ class PotusData(C.Structure):
 class PotusConfig(C.Structure):
     _fields_ = [
         ("chains", C.c_int32), ("chain_id_offset", C.c_int32), ("iter_warmup", C.c_int32), ("iter_sampling", C.c_int32),
-        ("keep_per_chain", C.c_int32), ("max_treedepth", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32),
+        ("keep_per_chain", C.c_int32), ("max_treedepth", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
         ("seed", C.c_uint64), ("adapt_delta", C.c_double), ("init_radius", C.c_double),
     ]
 
@@ -126,10 +126,10 @@ def marshal_data(data: dict):
 
 
 def make_config(chains=4, iter_warmup=500, iter_sampling=500, seed=1843, keep_per_chain=0, max_treedepth=10,
-                adapt_delta=0.8, init_radius=2.0, device=0, chain_id_offset=0) -> PotusConfig:
+                adapt_delta=0.8, init_radius=2.0, device=0, chain_id_offset=0, force_stream=False) -> PotusConfig:
     c = PotusConfig()
     c.chains, c.chain_id_offset, c.iter_warmup, c.iter_sampling = int(chains), int(chain_id_offset), int(iter_warmup), int(iter_sampling)
-    c.keep_per_chain, c.max_treedepth, c.device, c.reserved = int(keep_per_chain), int(max_treedepth), int(device), 0
+    c.keep_per_chain, c.max_treedepth, c.device, c.flags = int(keep_per_chain), int(max_treedepth), int(device), (1 if force_stream else 0)
     c.seed, c.adapt_delta, c.init_radius = int(seed), float(adapt_delta), float(init_radius)
     return c
 
@@ -137,7 +137,7 @@ def make_config(chains=4, iter_warmup=500, iter_sampling=500, seed=1843, keep_pe
 _lib = None
 
 EXPORTS = ("potus_create", "potus_run", "potus_draws_size", "potus_get_draws", "potus_get_stats",
-           "potus_device_buffer", "potus_destroy", "potus_last_error", "potus_logp_grad", "potus_num_params")
+           "potus_device_buffer", "potus_destroy", "potus_last_error", "potus_logp_grad", "potus_logp_grad_ex", "potus_num_params")
 
 
 def load_library(path: str | None = None):
@@ -169,6 +169,8 @@ def load_library(path: str | None = None):
     lib.potus_last_error.restype = C.c_char_p
     lib.potus_logp_grad.argtypes = [C.POINTER(PotusData), _f64p, C.c_int, _f64p, _f64p]
     lib.potus_logp_grad.restype = C.c_int
+    lib.potus_logp_grad_ex.argtypes = [C.POINTER(PotusData), _f64p, C.c_int, _f64p, _f64p, C.c_int]
+    lib.potus_logp_grad_ex.restype = C.c_int
     lib.potus_num_params.argtypes = [C.POINTER(PotusData)]
     lib.potus_num_params.restype = C.c_int
     if path is None:

@@ -12,6 +12,7 @@
 #include <vector>
 #include "../../include/potus_b200.h"
 #include "potus_layout.h"
+#include "potus_stream_layout.h"
 
 // (compiled as one translation unit with potus_kernel.cu through potus_lib.cu, which defines the kernels)
 using namespace potus;
@@ -425,8 +426,17 @@ constexpr int SMEM_BYTES = (int)SM_TOTAL + 128;
 
 }  // namespace
 
+#include "potus_stream_host.cuh"
+
 struct PotusSampler {
-  HostModel hm;
+  HostModel hm;       // resident kernel (potus_kernel.cu)
+  StreamHost sh;      // streaming kernel (potus_stream.cu): shapes the resident kernel does not hold
+  bool stream = false;
+  // what both paths share on the host: sizes, the vector length and the slot -> Stan index map
+  int S = 0, T = 0, P = 0, M = 0, Pop = 0, full = 0, D = 0, VL = 0;
+  double lp_const = 0;
+  const std::vector<int32_t>* map = nullptr;
+  float* rbuf = nullptr;
   PotusConfig cfg;
   int n_sm = 0, grid = 0, draw_len = 0, keep = 0, keep_every = 1;
   float *q = nullptr, *sqrt_m = nullptr, *wf_mean = nullptr, *wf_m2 = nullptr, *workspace = nullptr;
@@ -455,6 +465,8 @@ int potus_num_params(const PotusData* d) {
 void potus_destroy(PotusSampler* s) {
   if (!s) return;
   free_model(s->hm);
+  free_stream(s->sh);
+  cudaFree(s->rbuf);
   cudaFree(s->q); cudaFree(s->sqrt_m); cudaFree(s->wf_mean); cudaFree(s->wf_m2); cudaFree(s->workspace);
   cudaFree(s->cs); cudaFree(s->queue); cudaFree(s->draws); cudaFree(s->monitor); cudaFree(s->sparams); cudaFree(s->prof);
   delete s;
@@ -469,39 +481,56 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
     return fail(POTUS_ERR_STATE, "config: chains >= 1, iter_* >= 0, 1 <= max_treedepth <= 10 required");
   int rc = validate(data);
   if (rc) return rc;
-  rc = check_supported(data);
-  if (rc) return rc;
+  // kernel family: the resident kernel when the problem fits it (and config->reserved bit 0 does not force the streaming one)
+  const bool want_stream = (config->flags & POTUS_FLAG_FORCE_STREAM) != 0;
+  bool use_stream = want_stream;
+  if (!want_stream && check_supported(data) != POTUS_OK) use_stream = true;
+  if (use_stream && (rc = check_stream_supported(data))) return rc;
   int n_sm = 0;
   rc = check_device(config->device, &n_sm);
   if (rc) return rc;
   PotusSampler* s = new PotusSampler();
   s->cfg = *config;
   s->n_sm = n_sm;
-  rc = build_model(data, s->hm);
-  if (rc) { potus_destroy(s); return rc; }
-  const ModelDev& m = s->hm.m;
+  s->stream = use_stream;
+  if (use_stream) {
+    rc = build_stream_model(data, s->sh);
+    if (rc) { potus_destroy(s); return rc; }
+    const ModelS& ms = s->sh.m;
+    s->S = ms.S; s->T = ms.T; s->P = ms.P; s->M = ms.M; s->Pop = ms.Pop; s->full = ms.full; s->D = ms.D; s->VL = ms.VL;
+    s->lp_const = ms.lp_const; s->map = &s->sh.map_i2s;
+  } else {
+    rc = build_model(data, s->hm);
+    if (rc) { potus_destroy(s); return rc; }
+    const ModelDev& mr = s->hm.m;
+    s->S = mr.S; s->T = mr.T; s->P = mr.P; s->M = mr.M; s->Pop = mr.Pop; s->full = mr.full; s->D = mr.D; s->VL = VEC;
+    s->lp_const = mr.lp_const; s->map = &s->hm.map_i2s;
+  }
   const int C = config->chains;
   s->keep = config->keep_per_chain <= 0 ? config->iter_sampling : std::min(config->keep_per_chain, config->iter_sampling);
   s->keep_every = s->keep > 0 ? config->iter_sampling / s->keep : 1;
-  s->draw_len = m.S * m.T + m.P + s->hm.M + s->hm.Pop + m.T + m.S + m.D;
+  s->draw_len = s->S * s->T + s->P + s->M + s->Pop + s->T + s->S + s->D;
   s->grid = std::min(C, n_sm);
-  const size_t vb = (size_t)C * VEC * sizeof(float);
+  const size_t vb = (size_t)C * s->VL * sizeof(float);
   auto alloc = [&](void** p, size_t bytes) -> int {
     cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
     if (e != cudaSuccess) { char b[160]; snprintf(b, sizeof b, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e)); return fail(POTUS_ERR_CUDA, b); }
     return cudaMemset(*p, 0, std::max<size_t>(bytes, 16)) == cudaSuccess ? POTUS_OK : fail(POTUS_ERR_CUDA, "cudaMemset failed");
   };
   const int n_it = config->iter_warmup + config->iter_sampling;
+  const size_t ws_bytes = (size_t)s->grid * (use_stream ? SW_NSLOT : NSLOT) * s->VL * sizeof(float);
   if ((rc = alloc((void**)&s->q, vb)) || (rc = alloc((void**)&s->sqrt_m, vb)) || (rc = alloc((void**)&s->wf_mean, vb)) ||
-      (rc = alloc((void**)&s->wf_m2, vb)) || (rc = alloc((void**)&s->workspace, (size_t)s->grid * NSLOT * VEC * sizeof(float))) ||
+      (rc = alloc((void**)&s->wf_m2, vb)) || (rc = alloc((void**)&s->workspace, ws_bytes)) ||
+      (rc = alloc((void**)&s->rbuf, use_stream ? (size_t)s->grid * ((s->sh.N + 3) & ~3) * sizeof(float) : 16)) ||
       (rc = alloc((void**)&s->cs, (size_t)C * sizeof(ChainState))) || (rc = alloc((void**)&s->queue, sizeof(int))) ||
       (rc = alloc((void**)&s->draws, (size_t)C * s->keep * s->draw_len * sizeof(float))) ||
-      (rc = alloc((void**)&s->monitor, (size_t)C * config->iter_sampling * (m.S + 1) * sizeof(float))) ||
+      (rc = alloc((void**)&s->monitor, (size_t)C * config->iter_sampling * (s->S + 1) * sizeof(float))) ||
       (rc = alloc((void**)&s->sparams, (size_t)C * n_it * 8 * sizeof(float))) || (rc = alloc((void**)&s->prof, 64 * sizeof(unsigned long long)))) {
     potus_destroy(s);
     return rc;
   }
-  cudaError_t e = cudaFuncSetAttribute(potus_nuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = use_stream ? cudaFuncSetAttribute(potus_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SSMEM_BYTES)
+                             : cudaFuncSetAttribute(potus_nuts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   if (e != cudaSuccess) { potus_destroy(s); return fail(POTUS_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   *out = s;
   return POTUS_OK;
@@ -526,6 +555,20 @@ static RunArgs make_args(PotusSampler* s, int it0, int it1, int do_init) {
   return a;
 }
 
+static SRunArgs make_sargs(PotusSampler* s, int it0, int it1, int do_init) {
+  const RunArgs r = make_args(s, it0, it1, do_init);
+  SRunArgs a{};
+  a.m = s->sh.m;
+  a.n_chains = r.n_chains; a.chain_id_offset = r.chain_id_offset; a.iter_begin = it0; a.iter_end = it1;
+  a.iter_warmup = r.iter_warmup; a.iter_sampling = r.iter_sampling; a.max_depth = r.max_depth; a.do_init = do_init;
+  a.keep_every = r.keep_every; a.keep_per_chain = r.keep_per_chain; a.draw_len = r.draw_len;
+  a.w_init_buffer = r.w_init_buffer; a.w_term_buffer = r.w_term_buffer; a.w_base_window = r.w_base_window;
+  a.seed = r.seed; a.adapt_delta = r.adapt_delta; a.init_radius = r.init_radius;
+  a.q = s->q; a.sqrt_m = s->sqrt_m; a.wf_mean = s->wf_mean; a.wf_m2 = s->wf_m2; a.cs = s->cs; a.workspace = s->workspace; a.rbuf = s->rbuf;
+  a.queue = s->queue; a.draws = s->draws; a.monitor = s->monitor; a.sampler_params = s->sparams;
+  return a;
+}
+
 int potus_run(PotusSampler* s) {
   if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
@@ -536,16 +579,16 @@ int potus_run(PotusSampler* s) {
   CUDA_TRY(cudaEventRecord(e0));
   {
     CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
-    RunArgs a = make_args(s, 0, nw, 1);
-    potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(a);
+    if (s->stream) potus_stream_kernel<<<s->grid, SNT, SSMEM_BYTES>>>(make_sargs(s, 0, nw, 1));
+    else potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(make_args(s, 0, nw, 1));
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
   CUDA_TRY(cudaEventRecord(e1));
   if (nt > nw) {
     CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
-    RunArgs a = make_args(s, nw, nt, 0);
-    potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(a);
+    if (s->stream) potus_stream_kernel<<<s->grid, SNT, SSMEM_BYTES>>>(make_sargs(s, nw, nt, 0));
+    else potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(make_args(s, nw, nt, 0));
     CUDA_TRY(cudaGetLastError());
     ++launches;
   }
@@ -577,7 +620,7 @@ int potus_run(PotusSampler* s) {
   st.mean_accept_stat = acc / ns; st.mean_treedepth = dep / ns; st.mean_stepsize = eps / C;
   st.gpu_launches = launches;
   st.seconds_warmup = ms01 * 1e-3; st.seconds_sampling = ms12 * 1e-3; st.seconds_total = (ms01 + ms12) * 1e-3;
-  st.n_params = s->hm.m.D; st.n_draws_kept = C * s->keep;
+  st.n_params = s->D; st.n_draws_kept = C * s->keep;
 #ifdef POTUS_PROF
   {
     unsigned long long hp[64];
@@ -604,7 +647,7 @@ int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n) {
   const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling;
   switch (which) {
     case 0: *dptr = s->draws; *n = (size_t)C * s->keep * s->draw_len; break;
-    case 1: *dptr = s->monitor; *n = (size_t)C * s->cfg.iter_sampling * (s->hm.m.S + 1); break;
+    case 1: *dptr = s->monitor; *n = (size_t)C * s->cfg.iter_sampling * (s->S + 1); break;
     case 2: *dptr = s->sparams; *n = (size_t)C * nt * 8; break;
     default: return fail(POTUS_ERR_STATE, "unknown buffer id");
   }
@@ -613,18 +656,17 @@ int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n) {
 
 struct ParInfo { size_t off, len; bool exists; };
 static bool par_info(const PotusSampler* s, const char* par, ParInfo& pi) {
-  const ModelDev& m = s->hm.m;
-  const size_t ST = (size_t)m.S * m.T;
+  const size_t ST = (size_t)s->S * s->T;
   size_t o = 0;
   const std::string p = par ? par : "";
   auto hit = [&](const char* nm, size_t len, bool ex) { bool h = (p == nm); if (h) { pi.off = o; pi.len = len; pi.exists = ex; } o += len; return h; };
   if (hit("mu_b", ST, true)) return true;
-  if (hit("mu_c", m.P, true)) return true;
-  if (hit("mu_m", s->hm.M, s->hm.full)) return true;
-  if (hit("mu_pop", s->hm.Pop, s->hm.full)) return true;
-  if (hit("e_bias", m.T, s->hm.full)) return true;
-  if (hit("polling_bias", m.S, true)) return true;
-  if (hit("theta", m.D, true)) return true;
+  if (hit("mu_c", s->P, true)) return true;
+  if (hit("mu_m", s->M, s->full)) return true;
+  if (hit("mu_pop", s->Pop, s->full)) return true;
+  if (hit("e_bias", s->T, s->full)) return true;
+  if (hit("polling_bias", s->S, true)) return true;
+  if (hit("theta", s->D, true)) return true;
   return false;
 }
 
@@ -632,10 +674,10 @@ size_t potus_draws_size(const PotusSampler* s, const char* par) {
   if (!s || !par) return 0;
   const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling;
   const std::string p = par;
-  if (p == "monitor") return (size_t)C * s->cfg.iter_sampling * (s->hm.m.S + 1);
+  if (p == "monitor") return (size_t)C * s->cfg.iter_sampling * (s->S + 1);
   if (p == "sampler_params") return (size_t)C * nt * 7;
-  if (p == "inv_metric") return (size_t)C * s->hm.m.D;
-  if (p == "predicted_score") return (size_t)C * s->keep * s->hm.m.S * s->hm.m.T;
+  if (p == "inv_metric") return (size_t)C * s->D;
+  if (p == "predicted_score") return (size_t)C * s->keep * s->S * s->T;
   ParInfo pi;
   if (!par_info(s, par, pi) || !pi.exists) return 0;
   return (size_t)C * s->keep * pi.len;
@@ -648,11 +690,11 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   if (need == 0) return fail(POTUS_ERR_STATE, std::string("unknown quantity '") + par + "'");
   if (n < need) return fail(POTUS_ERR_STATE, "output buffer too small");
   CUDA_TRY(cudaSetDevice(s->cfg.device));
-  const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling, S = s->hm.m.S, T = s->hm.m.T;
+  const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling, S = s->S, T = s->T;
   const std::string p = par;
   if (p == "sampler_params") {  // [(iter)*chains, 7], row index = chain*nt + it (draw-fastest within a column)
     const size_t R = (size_t)C * nt;
-    const double c0 = s->hm.m.lp_const;  // device values are centred: lp__ = -U + c0, energy__ = H - c0
+    const double c0 = s->lp_const;  // device values are centred: lp__ = -U + c0, energy__ = H - c0
     for (size_t r = 0; r < R; ++r)
       for (int k = 0; k < 7; ++k) {
         double v = s->h_sparams[r * 8 + k];
@@ -663,12 +705,13 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
     return POTUS_OK;
   }
   if (p == "inv_metric") {  // adapted diagonal of M^-1 per chain, [chains, D] chain-fastest, Stan parameter order
-    std::vector<float> h((size_t)C * VEC);
+    const int VL = s->VL;
+    std::vector<float> h((size_t)C * VL);
     CUDA_TRY(cudaMemcpy(h.data(), s->sqrt_m, h.size() * sizeof(float), cudaMemcpyDeviceToHost));
     for (int c = 0; c < C; ++c)
-      for (int k = 0; k < VEC; ++k) {
-        const int si = s->hm.map_i2s[k];
-        if (si >= 0) { const double r = h[(size_t)c * VEC + k]; out[c + (size_t)C * si] = r * r; }
+      for (int k = 0; k < VL; ++k) {
+        const int si = (*s->map)[k];
+        if (si >= 0) { const double r = h[(size_t)c * VL + k]; out[c + (size_t)C * si] = r * r; }
       }
     return POTUS_OK;
   }
@@ -706,10 +749,61 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   return POTUS_OK;
 }
 
-int potus_logp_grad(const PotusData* data, const double* theta, int n, double* lp, double* grad) {
+// potus_logp_grad on the streaming kernel (shapes the resident kernel does not hold, or force_stream)
+static int logp_grad_stream(const PotusData* data, const double* theta, int n, double* lp, double* grad) {
+  StreamHost sh;
+  int rc = build_stream_model(data, sh);
+  if (rc) { free_stream(sh); return rc; }
+  const int D = sh.m.D, VL = sh.m.VL;
+  std::vector<float> qin((size_t)n * VL, 0.f);
+  for (int i = 0; i < n; ++i)
+    for (int k = 0; k < VL; ++k) {
+      int si = sh.map_i2s[k];
+      if (si >= 0) qin[(size_t)i * VL + k] = (float)theta[(size_t)i * D + si];
+    }
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+  const int grid = std::min(n, nsm);
+  float *dq = nullptr, *dg = nullptr, *dr = nullptr;
+  double* du = nullptr;
+  auto cleanup = [&]() { cudaFree(dq); cudaFree(dg); cudaFree(du); cudaFree(dr); free_stream(sh); };
+  cudaError_t e;
+  if ((e = cudaMalloc(&dq, qin.size() * 4)) != cudaSuccess || (e = cudaMalloc(&dg, qin.size() * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&du, (size_t)n * 8)) != cudaSuccess || (e = cudaMalloc(&dr, (size_t)grid * ((sh.N + 3) & ~3) * 4 + 16)) != cudaSuccess ||
+      (e = cudaMemcpy(dq, qin.data(), qin.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMemset(dg, 0, qin.size() * 4)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(potus_stream_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SSMEM_BYTES)) != cudaSuccess) {
+    cleanup();
+    return fail(POTUS_ERR_CUDA, cudaGetErrorString(e));
+  }
+  SEvalArgs a{};
+  a.m = sh.m; a.n = n; a.q_in = dq; a.g_out = dg; a.u_out = du; a.rbuf = dr;
+  potus_stream_eval_kernel<<<grid, SNT, SSMEM_BYTES>>>(a);
+  std::vector<float> g((size_t)n * VL);
+  std::vector<double> u(n);
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess || (e = cudaMemcpy(g.data(), dg, g.size() * 4, cudaMemcpyDeviceToHost)) != cudaSuccess ||
+      (e = cudaMemcpy(u.data(), du, (size_t)n * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) {
+    cleanup();
+    return fail(POTUS_ERR_CUDA, std::string("potus_stream_eval_kernel: ") + cudaGetErrorString(e));
+  }
+  for (int i = 0; i < n; ++i) {
+    lp[i] = -u[i] + sh.m.lp_const;
+    for (int k = 0; k < VL; ++k) {
+      int si = sh.map_i2s[k];
+      if (si >= 0) grad[(size_t)i * D + si] = -(double)g[(size_t)i * VL + k];
+    }
+  }
+  cleanup();
+  return POTUS_OK;
+}
+
+int potus_logp_grad_ex(const PotusData* data, const double* theta, int n, double* lp, double* grad, int force_stream) {
   if (!data || !theta || !lp || !grad || n < 1) return fail(POTUS_ERR_STATE, "NULL argument");
-  int rc = check_device(0, nullptr);
+  int rc = validate(data);
   if (rc) return rc;
+  rc = check_device(0, nullptr);
+  if (rc) return rc;
+  if (force_stream || check_supported(data) != POTUS_OK) return logp_grad_stream(data, theta, n, lp, grad);
   HostModel hm;
   rc = build_model(data, hm);
   if (rc) { free_model(hm); return rc; }
@@ -752,6 +846,10 @@ int potus_logp_grad(const PotusData* data, const double* theta, int n, double* l
   }
   cleanup();
   return POTUS_OK;
+}
+
+int potus_logp_grad(const PotusData* data, const double* theta, int n, double* lp, double* grad) {
+  return potus_logp_grad_ex(data, theta, n, lp, grad, 0);
 }
 
 }  // extern "C"

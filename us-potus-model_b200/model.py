@@ -144,7 +144,7 @@ class CmdStanModelB200:
     def sample(self, data: dict, seed: int = 1843, chains: int = 4, parallel_chains: int | None = None,
                iter_warmup: int = 500, iter_sampling: int = 500, refresh: int | None = None,
                adapt_delta: float = 0.8, max_treedepth: int = 10, keep_per_chain: int = 0, device: int = 0,
-               chain_id_offset: int = 0, init: float = 2.0) -> PotusFit:
+               chain_id_offset: int = 0, init: float = 2.0, force_stream: bool = False) -> PotusFit:
         """cmdstanr `$sample()` argument names; `parallel_chains`/`refresh` are accepted and ignored
         (all chains run concurrently on the GPU)."""
         lib = cabi.load_library()
@@ -157,7 +157,7 @@ class CmdStanModelB200:
         pd, keep = cabi.marshal_data(data)
         cfg = cabi.make_config(chains=chains, iter_warmup=iter_warmup, iter_sampling=iter_sampling, seed=seed,
                                keep_per_chain=keep_per_chain, max_treedepth=max_treedepth, adapt_delta=adapt_delta,
-                               init_radius=init, device=device, chain_id_offset=chain_id_offset)
+                               init_radius=init, device=device, chain_id_offset=chain_id_offset, force_stream=force_stream)
         h = C.c_void_p()
         cabi.check(lib, lib.potus_create(C.byref(pd), C.byref(cfg), C.byref(h)))
         try:
@@ -175,7 +175,7 @@ def cmdstan_model(stan_file: str | None = None, compile: bool = True, force: boo
     return CmdStanModelB200(stan_file)
 
 
-def logp_grad(data: dict, theta: np.ndarray):
+def logp_grad(data: dict, theta: np.ndarray, force_stream: bool = False):
     """Test hook (potus_logp_grad): lp and gradient on the device for theta[n, D] (Stan order)."""
     lib = cabi.load_library()
     pd, keep = cabi.marshal_data(data)
@@ -187,6 +187,7 @@ def logp_grad(data: dict, theta: np.ndarray):
     lp = np.empty(n)
     g = np.empty((n, D))
     f64p = C.POINTER(C.c_double)
-    cabi.check(lib, lib.potus_logp_grad(C.byref(pd), th.ctypes.data_as(f64p), n, lp.ctypes.data_as(f64p), g.ctypes.data_as(f64p)))
+    cabi.check(lib, lib.potus_logp_grad_ex(C.byref(pd), th.ctypes.data_as(f64p), n, lp.ctypes.data_as(f64p), g.ctypes.data_as(f64p),
+                                           1 if force_stream else 0))
     del keep
     return lp, g
