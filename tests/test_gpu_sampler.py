@@ -261,18 +261,19 @@ def test_no_metric_adaptation_below_20_warmup_iterations_on_device(pkg, orc_mod,
     r = orc_mod.OracleModel(d).sample(chains=2, iter_warmup=12, iter_sampling=3, seed=1843, threads=2, tree_mode=1)
     for c in range(2):
         assert np.all(sp["stepsize__"][c, 12:] == sp["stepsize__"][c, 12])
-        assert abs(sp["stepsize__"][c, 12] / r["stepsize"][c] - 1) < 0.02
+        assert abs(sp["stepsize__"][c, 12] / r["stepsize"][c] - 1) < 0.05   # exp(x_bar) of 12 noisy fp32-vs-fp64 accept_stats
         assert np.array_equal(sp["treedepth__"][c, :12], r["stats"][c, :12, 3])
 
 
 def test_adaptation_matches_oracle_distribution(pkg, datalists, cuda_lib):
     """SURVEY 8(a) row a12 against the oracle, past the first window: 296 device chains x 500 warm-up iterations vs the
     committed 64-chain fp64 oracle run (tests/golden/oracle_adaptation_2016.npz, make_oracle_adaptation.py; independent
-    chain ids, same law).  (i) per-coordinate mean over chains of log(inverse metric): |device - oracle| within 4 standard
-    errors of the difference (+1% slack), for every one of the 15098 coordinates; (ii) the final step size: means within
-    4 SE, spread within a factor 1.5; (iii) the step size restarts exactly after the window ends 99/149/249/449 (Stan
-    defaults 75/25/50): it moves by > 8% there in (almost) every chain -- init_stepsize + the reset of dual averaging --
-    and nowhere else late in a window; (iv) frozen after warm-up."""
+    chain ids, same law).  (i) per-coordinate mean over chains of log(inverse metric): |device - oracle| within 5 standard
+    errors of the difference (+1.5% slack), for every one of the 15098 coordinates; (ii) the final step size: means within
+    4 SE, spread within a factor 1.5; (iii) the dual-averaging recursion replayed from the recorded accept_stat__ reproduces
+    every recorded step size when -- and only when -- it is restarted exactly after the window ends 99/149/249/449 (Stan
+    defaults 75/25/50), the restart value being a power-of-two multiple (init_stepsize); (iv) frozen after warm-up; (v) the
+    mean step size per iteration tracks the oracle's through the whole warm-up."""
     d = datalists[2016]
     ora = np.load(os.path.join(GOLDEN, "oracle_adaptation_2016.npz"))
     C = 296
@@ -281,9 +282,10 @@ def test_adaptation_matches_oracle_distribution(pkg, datalists, cuda_lib):
     lm, ls = np.log(im).mean(0), np.log(im).std(0, ddof=1)
     n_o = int(ora["chains"])
     se = np.sqrt(ls ** 2 / C + ora["log_inv_metric_sd"].astype(np.float64) ** 2 / n_o)
-    z = np.abs(lm - ora["log_inv_metric_mean"]) / (4 * se + 0.01)
+    z = np.abs(lm - ora["log_inv_metric_mean"]) / (5 * se + 0.015)    # 15098 coordinates: the largest of that many |N(0,1)| is ~4.1
     print(f"a12: log inv-metric max z {z.max():.3f} (coordinate {int(z.argmax())}); median ratio {np.exp(np.median(lm - ora['log_inv_metric_mean'])):.4f}")
     assert z.max() <= 1.0, (z.max(), int(z.argmax()))
+    assert abs(np.median(lm - ora["log_inv_metric_mean"])) < 0.01
     sp = fit.sampler_params()
     eps_f = sp["stepsize__"][:, 500]
     eo = ora["stepsize"]
@@ -291,15 +293,30 @@ def test_adaptation_matches_oracle_distribution(pkg, datalists, cuda_lib):
     print(f"a12: final eps device {eps_f.mean():.5f} +- {eps_f.std(ddof=1):.5f}, oracle {eo.mean():.5f} +- {eo.std(ddof=1):.5f}")
     assert abs(eps_f.mean() - eo.mean()) <= 4 * se_e + 1e-4
     assert 1 / 1.5 < eps_f.std(ddof=1) / eo.std(ddof=1) < 1.5
+    # (iii) replay Stan's dual averaging from the RECORDED accept_stat__ with restarts exactly after iterations 99/149/249/449:
+    # every recorded step size must be reproduced (1e-3), the value after a window end must be the replayed value times an
+    # integer power of two (init_stepsize doubles / halves), and the frozen sampling step size must be exp(x_bar) of the last run
+    eps = sp["stepsize__"].astype(np.float64)
+    acc = np.minimum(1.0, sp["accept_stat__"].astype(np.float64))
+    mu = np.log(10 * eps[:, 0]); cnt = 0; sbar = np.zeros(C); xbar = np.zeros(C)
+    worst, worst_k = 0.0, 0.0
+    for it in range(500):
+        cnt += 1
+        eta = 1.0 / (cnt + 10)
+        sbar = (1 - eta) * sbar + eta * (0.8 - acc[:, it])
+        x = mu - sbar * np.sqrt(cnt) / 0.05
+        xe = cnt ** -0.75
+        xbar = (1 - xe) * xbar + xe * x
+        if it in (99, 149, 249, 449):
+            k = np.log2(eps[:, it + 1] / np.exp(x))
+            worst_k = max(worst_k, np.abs(k - np.rint(k)).max())
+            mu = np.log(10 * eps[:, it + 1]); cnt = 0; sbar = np.zeros(C); xbar = np.zeros(C)
+        elif it < 499:
+            worst = max(worst, np.abs(eps[:, it + 1] / np.exp(x) - 1).max())
+    print(f"a12: dual-averaging replay: worst relative step-size mismatch {worst:.2e}; worst distance of log2(restart ratio) from an integer {worst_k:.2e}")
+    assert worst < 1e-3 and worst_k < 2e-3
+    assert np.abs(eps[:, 500] / np.exp(xbar) - 1).max() < 1e-3
     eps = sp["stepsize__"][:, :500]
-    jump = np.abs(np.log(eps[:, 1:] / eps[:, :-1]))       # jump[:, k]: iteration k -> k+1
-    # after a window end the step size is re-initialised and dual averaging restarts from mu = log(10 eps): the FIRST
-    # learn_stepsize of the new run moves eps by a factor 10*exp(-(0.8-a)/(11*0.05)) in [2.3, 14] -- at wend+1 -> wend+2,
-    # in every chain, and (restart = counter reset) nowhere else is a move that large systematic
-    for wend in (99, 149, 249, 449):
-        assert (jump[:, wend + 1] > 0.7).mean() > 0.97, (wend, (jump[:, wend + 1] > 0.7).mean())
-    other = np.ones(499, bool); other[[100, 150, 250, 450]] = False; other[:100] = False
-    assert (jump[:, other] > 0.7).mean() < 0.01
     assert np.all(sp["stepsize__"][:, 500:] == sp["stepsize__"][:, 500:501])
     by_iter = np.abs(np.log(eps.mean(0)[100:] / ora["stepsize_by_iter"][100:500]))   # the whole adaptation path, not just its end:
     print(f"a12: mean step size by iteration vs oracle: median |log ratio| {np.median(by_iter):.3f}, max {by_iter.max():.3f}")
