@@ -32,11 +32,18 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES_PER_LEAPFROG = 4 * 15098 * 4          # read q,p + write q,p once, fp32 state (2016: 241 568 B)
-ALGO_FLOPS_PER_LEAPFROG = 4 * 51 * 51 * 254 + 20 * 1619 + 10 * 15098
-# dram__bytes_read.sum + dram__bytes_write.sum of potus_nuts_kernel from the ncu --set full capture in
-# profiles/r01_e_final_kernel.txt (25.435 GB over 286 391 leapfrogs): NUTS tree checkpoints, the state itself is on chip
-NCU_DRAM_BYTES_PER_LEAPFROG = 25.435008e9 / 286391
+# Workloads.  "2016" = BASELINE.json configs[1..3] (the configuration the metric is quoted on; resident kernel);
+# "syn" = configs[4], the synthetic S=256 x T=365 x N=50k stress problem of SURVEY.md 8(d) (streaming kernel family).
+# algo_bytes: SURVEY.md 8(d): read q,p + write q,p once, fp32 state = 4*D*4.  dram_bytes: dram__bytes_read.sum +
+# dram__bytes_write.sum per leapfrog of the kernel from the committed ncu --set full capture named in `ncu`.
+WORKLOADS = {
+    "2016": dict(D=15098, S=51, T=254, N=1619, kernel="potus_nuts_kernel", dram_bytes=25.435008e9 / 286391,
+                 ncu="profiles/r01_e_final_kernel.txt", desc="poll_model_2020.stan, 2016 data list (S=51,T=254,N=1619,D=15098)",
+                 data="2016 polls (reference data/all_polls.csv through the restated final_2016.R wrangling; committed fixture), random inits"),
+    "syn": dict(D=144837, S=256, T=365, N=50000, kernel="potus_stream_kernel", dram_bytes=None,
+                ncu="profiles/r02_stream_kernel.txt", desc="poll_model_2020.stan, synthetic list of SURVEY.md 8(d) (S=256,T=365,N=40000+10000,P=512,D=144837, seed 1843)",
+                data="synthetic (generator of SURVEY.md 8(d), numpy PCG64 seed 1843), random inits"),
+}
 
 
 def load_peaks():
@@ -142,9 +149,11 @@ def run_cpu(args, data, pkg, reference_line: bool):
     cores = usable_cores()
     iters = args.cpu_iters
 
+    depth = 10 if args.workload == "2016" else 6   # syn: a gradient costs ~50 ms on one core; bound the trees so the sample stays bounded
+
     def one(seed):
         r = om.sample(chains=cores, iter_warmup=args.iter_warmup, iter_sampling=args.iter_sampling, seed=seed, threads=cores,
-                      literal=True, tree_mode=0, max_iters=iters)
+                      literal=True, tree_mode=0, max_iters=iters, max_treedepth=depth)
         return int(r["n_leapfrog"].sum()), r["seconds"]
 
     if not reference_line:
@@ -160,11 +169,11 @@ def run_cpu(args, data, pkg, reference_line: bool):
         t_lf += lf; t_s += secs
     v = t_lf / t_s
     cb = {"value": v, "unit": "leapfrog/s", "cores": cores, "kind": "port",
-          "sample": f"each step: {cores} chains x first {iters} warm-up iterations (fp64 C restatement; rstan/CmdStan are not installable here)"}
+          "sample": f"each step: {cores} chains x first {iters} warm-up iterations, max_treedepth {depth} (fp64 C restatement; rstan/CmdStan are not installable here)"}
     return {"metric": "leapfrog steps/sec", "value": v, "unit": "leapfrog/s", "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "2016 polls from the reference's data/all_polls.csv (committed fixture)",
-            "config": {"workload": "poll_model_2020.stan, 2016 data list, Stan-default NUTS", "chains": cores,
+            "vs_baseline": None, "dtype": "f64", "data": WORKLOADS[args.workload]["data"],
+            "config": {"workload": WORKLOADS[args.workload]["desc"] + ", Stan-default NUTS", "chains": cores,
                        "iter_warmup": args.iter_warmup, "iter_sampling": args.iter_sampling, "bounded_iters_per_step": iters},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": "leapfrog/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
 
@@ -175,9 +184,10 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--chains", type=int, default=1024, help="chains per GPU (weak scaling)")
-    ap.add_argument("--iter-warmup", type=int, default=500)
-    ap.add_argument("--iter-sampling", type=int, default=500)
+    ap.add_argument("--workload", default="2016", choices=sorted(WORKLOADS), help="2016: BASELINE configs 2-4 (headline); syn: BASELINE config 5")
+    ap.add_argument("--chains", type=int, default=None, help="chains per GPU (weak scaling); default 1024 (2016) / 148 (syn)")
+    ap.add_argument("--iter-warmup", type=int, default=None, help="default 500 (2016) / 40 (syn: a step is a bounded slice of warm-up + sampling)")
+    ap.add_argument("--iter-sampling", type=int, default=None, help="default 500 (2016) / 10 (syn)")
     ap.add_argument("--keep-per-chain", type=int, default=3, help="full draws kept per chain (1024x3 ~ the reference's 6x500)")
     ap.add_argument("--seed", type=int, default=1843)
     ap.add_argument("--cpu-iters", type=int, default=10, help="bounded CPU sample: iterations per chain")
@@ -185,10 +195,17 @@ def main():
     ap.add_argument("--warmup-scale", type=float, default=0.1,
                     help="untimed warm-up steps run the same chains for this fraction of the iterations (clock/cache warm-up)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    dflt = {"2016": (1024, 500, 500), "syn": (148, 40, 10)}[args.workload]
+    args.chains = args.chains or dflt[0]
+    args.iter_warmup = dflt[1] if args.iter_warmup is None else args.iter_warmup
+    args.iter_sampling = dflt[2] if args.iter_sampling is None else args.iter_sampling
+    algo_bytes = 4 * wl["D"] * 4
+    gemm_flops = 4 * wl["S"] * wl["S"] * wl["T"]
 
     import potus_pkg
     pkg = potus_pkg.load()
-    data = pkg.load_npz(os.path.join(ROOT, "tests", "golden", "datalist_2016.npz"))
+    data = pkg.load_npz(os.path.join(ROOT, "tests", "golden", "datalist_2016.npz")) if args.workload == "2016" else pkg.synthetic_datalist()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -284,7 +301,7 @@ def main():
 
     peak, peak_src = load_peaks()
     value = lf / dev_s
-    ess_min, ess_med = ess_summary(pkg, res[-1]["monitor"])
+    ess_min, ess_med = ess_summary(pkg, res[-1]["monitor"]) if args.iter_sampling >= 50 else (float("nan"), float("nan"))
     run_s = res[-1]["dev_s"]
     samp_rate = lf_samp / samp_s if samp_s > 0 else float("nan")     # per-launch figure of the sampling-phase kernel
     per_gpu_rate = samp_rate / world
@@ -292,12 +309,12 @@ def main():
         "metric": "leapfrog steps/sec", "value": value, "unit": "leapfrog/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s / max(args.steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 state / fp16x2-split tensor-core GEMM with f32 accumulate / f64 energy reductions",
-        "data": "2016 polls (reference data/all_polls.csv through the restated final_2016.R wrangling; committed fixture), random inits",
-        "config": {"workload": "poll_model_2020.stan, 2016 data list (S=51,T=254,N=1619,D=15098), Stan-default NUTS "
-                               f"(diag_e, adapt_delta 0.8, max_treedepth 10), {args.iter_warmup}+{args.iter_sampling} iterations",
+        "data": wl["data"],
+        "config": {"workload": wl["desc"] + f", Stan-default NUTS (diag_e, adapt_delta 0.8, max_treedepth 10), {args.iter_warmup}+{args.iter_sampling} iterations",
                    "chains_per_gpu": args.chains, "chains_total": total_chains, "parallelism": f"chains sharded over {world} GPU(s), one all-gather of draws",
-                   "l2": "per-step working set (per-chain state 268 MB + tree workspace 368 MB per GPU) exceeds the 126 MB L2; "
-                         "chain state itself is SMEM/TMEM-resident"},
+                   "l2": ("per-step working set (per-chain state 268 MB + tree workspace 368 MB per GPU) exceeds the 126 MB L2; chain state itself is SMEM/TMEM-resident"
+                          if args.workload == "2016" else
+                          "per-step working set (tree workspace 26 MB per CTA x 148 + 2.3 MB per chain) exceeds the 126 MB L2; the state streams from HBM/L2 every leapfrog")},
         "ess_per_sec": {"min": ess_min / run_s * world, "median": ess_med / run_s * world, "quantities": "inv_logit-scale mu_b[,T] x51 + national",
                         "ess_min": ess_min, "ess_median": ess_med, "draws": int(np.prod(res[-1]["monitor"].shape[:2])),
                         "note": "ESS of this rank's chains over its run time (incl. warm-up), scaled by n_gpus"},
@@ -306,13 +323,16 @@ def main():
         "e2e": {"value": lf / e2e_s, "unit": "leapfrog/s", "h2d_bytes_per_step": int(res[-1]["h2d"]), "d2h_bytes_per_step": int(res[-1]["d2h"]),
                 "api": "cmdstan_model().sample(data=<host named list>) + extract(predicted_score) + monitor + sampler_params"},
         "gpu_launches": int(sum(r["launches"] for r in res)),
-        "roofline": {"bound": "hbm", "achieved": per_gpu_rate * ALGO_BYTES_PER_LEAPFROG / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": per_gpu_rate * ALGO_BYTES_PER_LEAPFROG / 1e9 / peak,
-                     "traffic": NCU_DRAM_BYTES_PER_LEAPFROG * (lf_samp / max(args.steps, 1) / world),
-                     "traffic_note": "bytes per sampling-phase launch = ncu DRAM bytes per leapfrog (profiles/r01_e_final_kernel.txt) x leapfrogs in the launch; algorithmic bytes per launch = 241568 x leapfrogs",
-                     "kernel": "potus_nuts_kernel (sampling-phase launch)", "peak_source": peak_src,
-                     "algorithmic_bytes_per_leapfrog": ALGO_BYTES_PER_LEAPFROG,
-                     "tensor_frac_of_bf16_peak": per_gpu_rate * 4 * 51 * 51 * 254 / 1700.3e12},
+        "roofline": {"bound": "hbm", "achieved": per_gpu_rate * algo_bytes / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": per_gpu_rate * algo_bytes / 1e9 / peak,
+                     "traffic": (wl["dram_bytes"] * (lf_samp / max(args.steps, 1) / world)) if wl["dram_bytes"] else None,
+                     "traffic_note": f"bytes per sampling-phase launch = ncu DRAM bytes per leapfrog ({wl['ncu']}) x leapfrogs in the launch; "
+                                     f"algorithmic bytes per launch = {algo_bytes} x leapfrogs",
+                     "kernel": wl["kernel"] + " (sampling-phase launch)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_leapfrog": algo_bytes,
+                     "tensor_frac_of_bf16_peak": per_gpu_rate * gemm_flops / 1700.3e12,
+                     "tensor_frac_note": "4 S^2 T dense flops per leapfrog (SURVEY.md 8(d)) / measured bf16 burst peak 1700.3 TF/s; the kernels issue 3 fp16 "
+                                         "products per GEMM (hi/lo split) on the lower-triangular half"},
         "clocks": clk, "wall_s_timed_region": t_wall,
     }
     if not args.no_cpu_baseline:

@@ -84,6 +84,10 @@ typedef struct PotusConfig {
   uint64_t seed;           /* default 1843 (final_2016.R:535) */
   double adapt_delta;      /* default 0.8 */
   double init_radius;      /* default 2.0: inits ~ U(-r, r) on the unconstrained scale */
+  int32_t n_gpus;          /* 0 / 1: this device only.  > 1: `chains` is the TOTAL; ONE process shards it contiguously over     */
+                           /* devices [device, device + n_gpus) (the reference's parallel_chains, final_2016.R:536), replicates */
+                           /* the read-only model, and potus_run ends with ONE ncclAllGather of the kept-draw buffers           */
+  int32_t reserved;
 } PotusConfig;
 
 #define POTUS_FLAG_FORCE_STREAM 1
@@ -101,6 +105,8 @@ typedef struct PotusStats {
   double mean_treedepth;
   int32_t n_params;              /* unconstrained dimension D                                */
   int32_t n_draws_kept;          /* chains * keep_per_chain                                  */
+  double seconds_gather;         /* n_gpus > 1: device time of the ncclAllGather (included in seconds_total; the other   */
+                                 /* seconds_* are the max over devices)                                              */
 } PotusStats;
 
 typedef struct PotusSampler PotusSampler;
@@ -123,7 +129,8 @@ POTUS_API size_t potus_draws_size(const PotusSampler* s, const char* par);
  *        under "# Diagonal elements of inverse mass matrix:"), Stan unconstrained order               */
 POTUS_API int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
 POTUS_API int potus_get_stats(PotusSampler* s, PotusStats* stats);
-/* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py):
+/* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py; with n_gpus > 1, which = 0
+ * is the all-gathered buffer on the first device, [n_gpus][ceil(chains/n_gpus)*keep][draw_len], and 1 / 2 are not available):
  *   which = 0: kept draws   [chains*keep][draw_len]   (draw_len floats per draw, Stan block order:
  *              mu_b | mu_c | mu_m | mu_pop | e_bias | polling_bias | theta)
  *   which = 1: monitor      [chains][iter_sampling][S+1]

@@ -90,6 +90,7 @@ SEXP potus_nuts_sample(SEXP data, SEXP config) {
   c.max_treedepth = (int32_t)scalar(config, "max_treedepth", 10); c.device = (int32_t)scalar(config, "device", 0);
   c.seed = (uint64_t)scalar(config, "seed", 1843); c.adapt_delta = scalar(config, "adapt_delta", 0.8);
   c.init_radius = scalar(config, "init", 2.0); c.chain_id_offset = (int32_t)scalar(config, "chain_id_offset", 0);
+  c.n_gpus = (int32_t)scalar(config, "n_gpus", 1);   /* > 1: the library shards the chains over that many devices and all-gathers the draws */
 
   char err[512]; err[0] = 0;
   PotusSampler* s = NULL;

@@ -321,3 +321,26 @@ def test_adaptation_matches_oracle_distribution(pkg, datalists, cuda_lib):
     by_iter = np.abs(np.log(eps.mean(0)[100:] / ora["stepsize_by_iter"][100:500]))   # the whole adaptation path, not just its end:
     print(f"a12: mean step size by iteration vs oracle: median |log ratio| {np.median(by_iter):.3f}, max {by_iter.max():.3f}")
     assert np.median(by_iter) < 0.06 and by_iter.max() < 0.3     # per-iteration eps has ~30% spread; oracle mean is over 64 chains
+
+
+def test_in_library_multi_gpu_is_the_same_chains(pkg, datalists, cuda_lib):
+    """PotusConfig.n_gpus: ONE process, chains sharded over the devices, one ncclAllGather of the kept draws
+    inside potus_run.  Every chain must be bit-identical to the single-device run (RNG streams are keyed by global chain id)
+    and every output must come back in global chain order.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    d = datalists[2008]
+    m = pkg.cmdstan_model()
+    kw = dict(data=d, seed=7, iter_warmup=25, iter_sampling=6, keep_per_chain=2)
+    one = m.sample(chains=7, **kw)                 # 7 chains over 2 devices: shards of 4 and 3 (unequal: the gather pads)
+    two = m.sample(chains=7, n_gpus=2, **kw)
+    assert two.stats["n_draws_kept"] == 14 and two.stats["gpu_launches"] == 4 and two.stats["seconds_gather"] > 0
+    assert np.array_equal(one.theta(), two.theta())
+    assert np.array_equal(one.extract("mu_b"), two.extract("mu_b")) and np.array_equal(one.extract("polling_bias"), two.extract("polling_bias"))
+    assert np.array_equal(one.monitor(), two.monitor())
+    a, b = one.sampler_params(), two.sampler_params()
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(one.inv_metric(), two.inv_metric())
+    assert one.stats["n_leapfrog_total"] == two.stats["n_leapfrog_total"]

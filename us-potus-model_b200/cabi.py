@@ -39,6 +39,7 @@ class PotusConfig(C.Structure):
         ("chains", C.c_int32), ("chain_id_offset", C.c_int32), ("iter_warmup", C.c_int32), ("iter_sampling", C.c_int32),
         ("keep_per_chain", C.c_int32), ("max_treedepth", C.c_int32), ("device", C.c_int32), ("flags", C.c_int32),
         ("seed", C.c_uint64), ("adapt_delta", C.c_double), ("init_radius", C.c_double),
+        ("n_gpus", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -48,7 +49,7 @@ class PotusStats(C.Structure):
         ("gpu_launches", C.c_int64),
         ("seconds_total", C.c_double), ("seconds_warmup", C.c_double), ("seconds_sampling", C.c_double),
         ("mean_stepsize", C.c_double), ("mean_accept_stat", C.c_double), ("mean_treedepth", C.c_double),
-        ("n_params", C.c_int32), ("n_draws_kept", C.c_int32),
+        ("n_params", C.c_int32), ("n_draws_kept", C.c_int32), ("seconds_gather", C.c_double),
     ]
 
 
@@ -126,11 +127,12 @@ def marshal_data(data: dict):
 
 
 def make_config(chains=4, iter_warmup=500, iter_sampling=500, seed=1843, keep_per_chain=0, max_treedepth=10,
-                adapt_delta=0.8, init_radius=2.0, device=0, chain_id_offset=0, force_stream=False) -> PotusConfig:
+                adapt_delta=0.8, init_radius=2.0, device=0, chain_id_offset=0, force_stream=False, n_gpus=1) -> PotusConfig:
     c = PotusConfig()
     c.chains, c.chain_id_offset, c.iter_warmup, c.iter_sampling = int(chains), int(chain_id_offset), int(iter_warmup), int(iter_sampling)
     c.keep_per_chain, c.max_treedepth, c.device, c.flags = int(keep_per_chain), int(max_treedepth), int(device), (1 if force_stream else 0)
     c.seed, c.adapt_delta, c.init_radius = int(seed), float(adapt_delta), float(init_radius)
+    c.n_gpus, c.reserved = int(n_gpus), 0
     return c
 
 

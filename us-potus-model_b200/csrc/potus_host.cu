@@ -3,6 +3,8 @@
 // task lists, owner-layout maps), launches, and output reshaping to rstan::extract's layout.
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -428,6 +430,43 @@ constexpr int SMEM_BYTES = (int)SM_TOTAL + 128;
 
 #include "potus_stream_host.cuh"
 
+// ---- NCCL, resolved at run time (dlopen): the library loads and runs single-GPU without it; n_gpus > 1 needs libnccl.so.2
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  if (api.h) return &api;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return nullptr;
+  api.CommInitAll = (decltype(api.CommInitAll))dlsym(h, "ncclCommInitAll");
+  api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+  if (!api.CommInitAll || !api.AllGather || !api.CommDestroy || !api.GetErrorString || !api.GroupStart || !api.GroupEnd) return nullptr;
+  api.h = h;
+  return &api;
+}
+void nccl_destroy_all(std::vector<ncclComm_t>& comms) {
+  NcclApi* n = nccl_api();
+  if (n) for (ncclComm_t c : comms) if (c) n->CommDestroy(c);
+  comms.clear();
+}
+thread_local int g_alloc_chains_hint = 0;   // create_multi: every shard's draw buffer is sized for the largest shard
+}  // namespace
+struct PotusSampler;
+static int create_multi(const PotusData* data, const PotusConfig* config, PotusSampler** out);
+
 struct PotusSampler {
   HostModel hm;       // resident kernel (potus_kernel.cu)
   StreamHost sh;      // streaming kernel (potus_stream.cu): shapes the resident kernel does not hold
@@ -437,6 +476,15 @@ struct PotusSampler {
   double lp_const = 0;
   const std::vector<int32_t>* map = nullptr;
   float* rbuf = nullptr;
+  // n_gpus > 1: this object is the parent of one sub-sampler per device (single process); `gath` holds, on every device, the
+  // all-gathered kept-draw buffer [n_gpus][pad_draws][draw_len]
+  std::vector<PotusSampler*> subs;
+  std::vector<ncclComm_t> comms;
+  std::vector<float*> gath;
+  size_t pad_floats = 0;
+  int alloc_chains = 0;         // chains the draw buffer is sized for (>= chains; equal shard size for ncclAllGather)
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  int launches = 0;
   PotusConfig cfg;
   int n_sm = 0, grid = 0, draw_len = 0, keep = 0, keep_every = 1;
   float *q = nullptr, *sqrt_m = nullptr, *wf_mean = nullptr, *wf_m2 = nullptr, *workspace = nullptr;
@@ -449,6 +497,65 @@ struct PotusSampler {
   std::vector<float> h_draws, h_monitor, h_sparams;
   bool have_host = false;
 };
+
+// contiguous shard of `total` chains for part `rank` of `world` (the same rule bench.py's torchrun path uses)
+static void shard_of(int total, int world, int rank, int* off, int* n) {
+  const int base = total / world, rem = total % world;
+  *n = base + (rank < rem ? 1 : 0);
+  *off = rank * base + std::min(rank, rem);
+}
+
+extern "C" int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
+extern "C" void potus_destroy(PotusSampler* s);
+
+// n_gpus > 1: ONE process, chains sharded contiguously over devices [device, device + n_gpus), the read-only
+// model replicated on each, one ncclCommInitAll, and after sampling ONE ncclAllGather of the kept-draw buffers.
+static int create_multi(const PotusData* data, const PotusConfig* config, PotusSampler** out) {
+  const int G = config->n_gpus;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(POTUS_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+  if (config->device < 0 || config->device + G > count) {
+    char b[160]; snprintf(b, sizeof b, "n_gpus = %d from device %d needs devices up to %d, but %d are visible", G, config->device, config->device + G - 1, count);
+    return fail(POTUS_ERR_CUDA, b);
+  }
+  if (config->chains < G) return fail(POTUS_ERR_STATE, "config: chains >= n_gpus required");
+  NcclApi* nc = nccl_api();
+  if (!nc) return fail(POTUS_ERR_CUDA, "n_gpus > 1 needs NCCL (libnccl.so.2 could not be loaded)");
+  PotusSampler* s = new PotusSampler();
+  s->cfg = *config;
+  int maxn = 0;
+  for (int d = 0; d < G; ++d) { int off, n; shard_of(config->chains, G, d, &off, &n); maxn = std::max(maxn, n); }
+  for (int d = 0; d < G; ++d) {
+    int off, n;
+    shard_of(config->chains, G, d, &off, &n);
+    PotusConfig c = *config;
+    c.n_gpus = 1; c.device = config->device + d; c.chains = n; c.chain_id_offset = config->chain_id_offset + off;
+    PotusSampler* sub = nullptr;
+    g_alloc_chains_hint = maxn;
+    int rc = potus_create(data, &c, &sub);
+    g_alloc_chains_hint = 0;
+    if (rc) { const std::string msg = g_err; potus_destroy(s); return fail(rc, msg); }
+    s->subs.push_back(sub);
+  }
+  const PotusSampler* s0 = s->subs[0];
+  s->stream = s0->stream; s->S = s0->S; s->T = s0->T; s->P = s0->P; s->M = s0->M; s->Pop = s0->Pop; s->full = s0->full; s->D = s0->D; s->VL = s0->VL;
+  s->lp_const = s0->lp_const; s->keep = s0->keep; s->keep_every = s0->keep_every; s->draw_len = s0->draw_len;
+  s->pad_floats = (size_t)maxn * s->keep * s->draw_len;
+  s->gath.assign(G, nullptr);
+  for (int d = 0; d < G; ++d) {
+    cudaSetDevice(config->device + d);
+    cudaError_t e = cudaMalloc((void**)&s->gath[d], std::max<size_t>(s->pad_floats * G * sizeof(float), 16));
+    if (e != cudaSuccess) { potus_destroy(s); return fail(POTUS_ERR_CUDA, std::string("cudaMalloc of the all-gather buffer: ") + cudaGetErrorString(e)); }
+  }
+  std::vector<int> devs(G);
+  for (int d = 0; d < G; ++d) devs[d] = config->device + d;
+  s->comms.assign(G, nullptr);
+  ncclResult_t r = nc->CommInitAll(s->comms.data(), G, devs.data());
+  if (r != ncclSuccess) { const std::string m = std::string("ncclCommInitAll: ") + nc->GetErrorString(r); potus_destroy(s); return fail(POTUS_ERR_CUDA, m); }
+  *out = s;
+  return POTUS_OK;
+}
 
 extern "C" {
 
@@ -464,6 +571,18 @@ int potus_num_params(const PotusData* d) {
 
 void potus_destroy(PotusSampler* s) {
   if (!s) return;
+  if (!s->subs.empty()) {
+    for (size_t d = 0; d < s->subs.size(); ++d) {
+      cudaSetDevice(s->subs[d]->cfg.device);
+      if (d < s->gath.size()) cudaFree(s->gath[d]);
+    }
+    nccl_destroy_all(s->comms);
+    for (PotusSampler* q : s->subs) potus_destroy(q);
+    delete s;
+    return;
+  }
+  cudaSetDevice(s->cfg.device);
+  for (int i = 0; i < 3; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
   free_model(s->hm);
   free_stream(s->sh);
   cudaFree(s->rbuf);
@@ -481,6 +600,7 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
     return fail(POTUS_ERR_STATE, "config: chains >= 1, iter_* >= 0, 1 <= max_treedepth <= 10 required");
   int rc = validate(data);
   if (rc) return rc;
+  if (config->n_gpus > 1) return create_multi(data, config, out);
   // kernel family: the resident kernel when the problem fits it (and config->reserved bit 0 does not force the streaming one)
   const bool want_stream = (config->flags & POTUS_FLAG_FORCE_STREAM) != 0;
   bool use_stream = want_stream;
@@ -507,6 +627,7 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
     s->lp_const = mr.lp_const; s->map = &s->hm.map_i2s;
   }
   const int C = config->chains;
+  s->alloc_chains = std::max(C, g_alloc_chains_hint);
   s->keep = config->keep_per_chain <= 0 ? config->iter_sampling : std::min(config->keep_per_chain, config->iter_sampling);
   s->keep_every = s->keep > 0 ? config->iter_sampling / s->keep : 1;
   s->draw_len = s->S * s->T + s->P + s->M + s->Pop + s->T + s->S + s->D;
@@ -521,9 +642,9 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
   const size_t ws_bytes = (size_t)s->grid * (use_stream ? SW_NSLOT : NSLOT) * s->VL * sizeof(float);
   if ((rc = alloc((void**)&s->q, vb)) || (rc = alloc((void**)&s->sqrt_m, vb)) || (rc = alloc((void**)&s->wf_mean, vb)) ||
       (rc = alloc((void**)&s->wf_m2, vb)) || (rc = alloc((void**)&s->workspace, ws_bytes)) ||
-      (rc = alloc((void**)&s->rbuf, use_stream ? (size_t)s->grid * ((s->sh.N + 3) & ~3) * sizeof(float) : 16)) ||
+      (rc = alloc((void**)&s->rbuf, use_stream ? (size_t)s->grid * s->sh.m.rb_len * sizeof(float) : 16)) ||
       (rc = alloc((void**)&s->cs, (size_t)C * sizeof(ChainState))) || (rc = alloc((void**)&s->queue, sizeof(int))) ||
-      (rc = alloc((void**)&s->draws, (size_t)C * s->keep * s->draw_len * sizeof(float))) ||
+      (rc = alloc((void**)&s->draws, (size_t)s->alloc_chains * s->keep * s->draw_len * sizeof(float))) ||
       (rc = alloc((void**)&s->monitor, (size_t)C * config->iter_sampling * (s->S + 1) * sizeof(float))) ||
       (rc = alloc((void**)&s->sparams, (size_t)C * n_it * 8 * sizeof(float))) || (rc = alloc((void**)&s->prof, 64 * sizeof(unsigned long long)))) {
     potus_destroy(s);
@@ -566,38 +687,45 @@ static SRunArgs make_sargs(PotusSampler* s, int it0, int it1, int do_init) {
   a.seed = r.seed; a.adapt_delta = r.adapt_delta; a.init_radius = r.init_radius;
   a.q = s->q; a.sqrt_m = s->sqrt_m; a.wf_mean = s->wf_mean; a.wf_m2 = s->wf_m2; a.cs = s->cs; a.workspace = s->workspace; a.rbuf = s->rbuf;
   a.queue = s->queue; a.draws = s->draws; a.monitor = s->monitor; a.sampler_params = s->sparams;
+  a.prof = s->prof;
   return a;
 }
 
-int potus_run(PotusSampler* s) {
-  if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
+// enqueue the warm-up and the sampling launch on the sampler's device (asynchronous)
+static int run_launch(PotusSampler* s) {
   CUDA_TRY(cudaSetDevice(s->cfg.device));
-  cudaEvent_t e0, e1, e2;
-  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventCreate(&e2));
+  for (int i = 0; i < 3; ++i) if (!s->ev[i]) CUDA_TRY(cudaEventCreate(&s->ev[i]));
   const int nw = s->cfg.iter_warmup, nt = nw + s->cfg.iter_sampling;
-  int launches = 0;
-  CUDA_TRY(cudaEventRecord(e0));
+  s->launches = 0;
+  CUDA_TRY(cudaMemsetAsync(s->prof, 0, 64 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaEventRecord(s->ev[0]));
   {
     CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
     if (s->stream) potus_stream_kernel<<<s->grid, SNT, SSMEM_BYTES>>>(make_sargs(s, 0, nw, 1));
     else potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(make_args(s, 0, nw, 1));
     CUDA_TRY(cudaGetLastError());
-    ++launches;
+    ++s->launches;
   }
-  CUDA_TRY(cudaEventRecord(e1));
+  CUDA_TRY(cudaEventRecord(s->ev[1]));
   if (nt > nw) {
     CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
     if (s->stream) potus_stream_kernel<<<s->grid, SNT, SSMEM_BYTES>>>(make_sargs(s, nw, nt, 0));
     else potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(make_args(s, nw, nt, 0));
     CUDA_TRY(cudaGetLastError());
-    ++launches;
+    ++s->launches;
   }
-  CUDA_TRY(cudaEventRecord(e2));
-  CUDA_TRY(cudaEventSynchronize(e2));
+  CUDA_TRY(cudaEventRecord(s->ev[2]));
+  return POTUS_OK;
+}
+
+// wait for the launches of run_launch and form the summary statistics
+static int run_finish(PotusSampler* s) {
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  const int nw = s->cfg.iter_warmup, nt = nw + s->cfg.iter_sampling;
+  CUDA_TRY(cudaEventSynchronize(s->ev[2]));
   CUDA_TRY(cudaGetLastError());
   float ms01 = 0, ms12 = 0;
-  CUDA_TRY(cudaEventElapsedTime(&ms01, e0, e1)); CUDA_TRY(cudaEventElapsedTime(&ms12, e1, e2));
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  CUDA_TRY(cudaEventElapsedTime(&ms01, s->ev[0], s->ev[1])); CUDA_TRY(cudaEventElapsedTime(&ms12, s->ev[1], s->ev[2]));
   // summary statistics from the per-iteration sampler diagnostics
   const int C = s->cfg.chains;
   s->h_sparams.resize((size_t)C * nt * 8);
@@ -618,21 +746,77 @@ int potus_run(PotusSampler* s) {
   }
   const double ns = (double)C * std::max(1, nt - nw);
   st.mean_accept_stat = acc / ns; st.mean_treedepth = dep / ns; st.mean_stepsize = eps / C;
-  st.gpu_launches = launches;
+  st.gpu_launches = s->launches;
   st.seconds_warmup = ms01 * 1e-3; st.seconds_sampling = ms12 * 1e-3; st.seconds_total = (ms01 + ms12) * 1e-3;
   st.n_params = s->D; st.n_draws_kept = C * s->keep;
 #ifdef POTUS_PROF
   {
     unsigned long long hp[64];
     if (cudaMemcpy(hp, s->prof, sizeof hp, cudaMemcpyDeviceToHost) == cudaSuccess) {
-      fprintf(stderr, "[potus_prof] leaves=%llu cycles/leaf per phase (thread 0, summed over CTAs):", hp[39]);
-      for (int i = 0; i < 24; ++i) fprintf(stderr, " p%d=%.0f", i, hp[39] ? (double)hp[i] / (double)hp[39] : 0.0);
+      const unsigned long long nl = s->stream ? hp[31] : hp[39];
+      fprintf(stderr, "[potus_prof] leaves=%llu cycles/leaf per phase (thread 0, summed over CTAs):", nl);
+      for (int i = 0; i < 24; ++i) fprintf(stderr, " p%d=%.0f", i, nl ? (double)hp[i] / (double)nl : 0.0);
       fprintf(stderr, "\n");
     }
   }
 #endif
   s->ran = true; s->have_host = false;
   return POTUS_OK;
+}
+
+static int run_multi(PotusSampler* s) {
+  NcclApi* nc = nccl_api();
+  const int G = (int)s->subs.size();
+  int rc;
+  for (PotusSampler* q : s->subs) if ((rc = run_launch(q))) return rc;      // all devices run concurrently
+  for (PotusSampler* q : s->subs) if ((rc = run_finish(q))) return rc;
+  // the path's one exchange: all-gather of the kept draws over NVLink
+  cudaEvent_t g0, g1;
+  CUDA_TRY(cudaSetDevice(s->subs[0]->cfg.device));
+  CUDA_TRY(cudaEventCreate(&g0)); CUDA_TRY(cudaEventCreate(&g1));
+  CUDA_TRY(cudaEventRecord(g0));
+  float gms = 0.f;
+  if (s->pad_floats > 0) {
+    ncclResult_t r = nc->GroupStart();
+    for (int d = 0; d < G && r == ncclSuccess; ++d) {
+      CUDA_TRY(cudaSetDevice(s->subs[d]->cfg.device));
+      r = nc->AllGather(s->subs[d]->draws, s->gath[d], s->pad_floats, ncclFloat, s->comms[d], 0);
+    }
+    if (r == ncclSuccess) r = nc->GroupEnd();
+    if (r != ncclSuccess) return fail(POTUS_ERR_CUDA, std::string("ncclAllGather: ") + nc->GetErrorString(r));
+  }
+  CUDA_TRY(cudaSetDevice(s->subs[0]->cfg.device));
+  CUDA_TRY(cudaEventRecord(g1));
+  for (int d = 0; d < G; ++d) { CUDA_TRY(cudaSetDevice(s->subs[d]->cfg.device)); CUDA_TRY(cudaDeviceSynchronize()); }
+  CUDA_TRY(cudaSetDevice(s->subs[0]->cfg.device));
+  CUDA_TRY(cudaEventElapsedTime(&gms, g0, g1));
+  cudaEventDestroy(g0); cudaEventDestroy(g1);
+  PotusStats& st = s->stats;
+  st = PotusStats{};
+  double acc = 0, dep = 0, eps = 0, tw = 0, ts = 0, tt = 0;
+  int C = 0;
+  for (PotusSampler* q : s->subs) {
+    const PotusStats& a = q->stats;
+    const int c = q->cfg.chains;
+    st.n_leapfrog_total += a.n_leapfrog_total; st.n_leapfrog_sampling += a.n_leapfrog_sampling; st.n_divergent_sampling += a.n_divergent_sampling;
+    st.gpu_launches += a.gpu_launches;
+    acc += a.mean_accept_stat * c; dep += a.mean_treedepth * c; eps += a.mean_stepsize * c; C += c;
+    tw = std::max(tw, a.seconds_warmup); ts = std::max(ts, a.seconds_sampling); tt = std::max(tt, a.seconds_total);
+  }
+  st.mean_accept_stat = acc / C; st.mean_treedepth = dep / C; st.mean_stepsize = eps / C;
+  st.seconds_warmup = tw; st.seconds_sampling = ts; st.seconds_total = tt + gms * 1e-3;   // max over devices + the gather
+  st.seconds_gather = gms * 1e-3;
+  st.n_params = s->D; st.n_draws_kept = C * s->keep;
+  s->ran = true; s->have_host = false;
+  return POTUS_OK;
+}
+
+int potus_run(PotusSampler* s) {
+  if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
+  if (!s->subs.empty()) return run_multi(s);
+  int rc = run_launch(s);
+  if (rc) return rc;
+  return run_finish(s);
 }
 
 int potus_get_stats(PotusSampler* s, PotusStats* out) {
@@ -645,6 +829,11 @@ int potus_get_stats(PotusSampler* s, PotusStats* out) {
 int potus_device_buffer(PotusSampler* s, int which, void** dptr, size_t* n) {
   if (!s || !dptr || !n) return fail(POTUS_ERR_STATE, "NULL argument");
   const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling;
+  if (!s->subs.empty()) {
+    if (which != 0) return fail(POTUS_ERR_STATE, "n_gpus > 1: only the all-gathered draw buffer (which = 0) is exposed");
+    *dptr = s->gath[0]; *n = s->pad_floats * s->subs.size();
+    return POTUS_OK;
+  }
   switch (which) {
     case 0: *dptr = s->draws; *n = (size_t)C * s->keep * s->draw_len; break;
     case 1: *dptr = s->monitor; *n = (size_t)C * s->cfg.iter_sampling * (s->S + 1); break;
@@ -689,9 +878,41 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   const size_t need = potus_draws_size(s, par);
   if (need == 0) return fail(POTUS_ERR_STATE, std::string("unknown quantity '") + par + "'");
   if (n < need) return fail(POTUS_ERR_STATE, "output buffer too small");
-  CUDA_TRY(cudaSetDevice(s->cfg.device));
   const int C = s->cfg.chains, nt = s->cfg.iter_warmup + s->cfg.iter_sampling, S = s->S, T = s->T;
   const std::string p = par;
+  if (!s->subs.empty()) {
+    if (p == "sampler_params" || p == "monitor" || p == "inv_metric") {
+      // per-chain quantities: every shard answers for its own chains; rows are ordered by global chain id
+      const size_t K = p == "sampler_params" ? 7 : (p == "monitor" ? (size_t)S + 1 : (size_t)s->D);
+      const size_t rows_per_chain = p == "sampler_params" ? (size_t)nt : (p == "monitor" ? (size_t)s->cfg.iter_sampling : 1);
+      const size_t R = (size_t)C * rows_per_chain;
+      size_t row0 = 0;
+      std::vector<double> tmp;
+      for (PotusSampler* q : s->subs) {
+        const size_t Rd = (size_t)q->cfg.chains * rows_per_chain;
+        tmp.resize(Rd * K);
+        int rc = potus_get_draws(q, par, tmp.data(), tmp.size());
+        if (rc) return rc;
+        for (size_t k = 0; k < K; ++k)
+          for (size_t r = 0; r < Rd; ++r) out[row0 + r + R * k] = tmp[r + Rd * k];
+        row0 += Rd;
+      }
+      return POTUS_OK;
+    }
+    if (!s->have_host) {   // kept draws of ALL chains from the first device's all-gathered buffer
+      CUDA_TRY(cudaSetDevice(s->subs[0]->cfg.device));
+      s->h_draws.resize((size_t)C * s->keep * s->draw_len);
+      size_t o = 0;
+      for (size_t d = 0; d < s->subs.size(); ++d) {
+        const size_t nd = (size_t)s->subs[d]->cfg.chains * s->keep * s->draw_len;
+        if (nd) CUDA_TRY(cudaMemcpy(s->h_draws.data() + o, s->gath[0] + d * s->pad_floats, nd * sizeof(float), cudaMemcpyDeviceToHost));
+        o += nd;
+      }
+      s->have_host = true;
+    }
+  } else {
+    CUDA_TRY(cudaSetDevice(s->cfg.device));
+  }
   if (p == "sampler_params") {  // [(iter)*chains, 7], row index = chain*nt + it (draw-fastest within a column)
     const size_t R = (size_t)C * nt;
     const double c0 = s->lp_const;  // device values are centred: lp__ = -U + c0, energy__ = H - c0
@@ -769,7 +990,7 @@ static int logp_grad_stream(const PotusData* data, const double* theta, int n, d
   auto cleanup = [&]() { cudaFree(dq); cudaFree(dg); cudaFree(du); cudaFree(dr); free_stream(sh); };
   cudaError_t e;
   if ((e = cudaMalloc(&dq, qin.size() * 4)) != cudaSuccess || (e = cudaMalloc(&dg, qin.size() * 4)) != cudaSuccess ||
-      (e = cudaMalloc(&du, (size_t)n * 8)) != cudaSuccess || (e = cudaMalloc(&dr, (size_t)grid * ((sh.N + 3) & ~3) * 4 + 16)) != cudaSuccess ||
+      (e = cudaMalloc(&du, (size_t)n * 8)) != cudaSuccess || (e = cudaMalloc(&dr, (size_t)grid * sh.m.rb_len * 4)) != cudaSuccess || (e = cudaMemset(dr, 0, (size_t)grid * sh.m.rb_len * 4)) != cudaSuccess ||
       (e = cudaMemcpy(dq, qin.data(), qin.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
       (e = cudaMemset(dg, 0, qin.size() * 4)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(potus_stream_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SSMEM_BYTES)) != cudaSuccess) {

@@ -36,8 +36,19 @@ struct SCtl {
   double U_samp, H_samp, U_prop, H_prop;
   float sum_metro;
   int pad1;
+#ifdef POTUS_PROF
+  unsigned long long prof[32];
+#endif
 };
 static_assert(sizeof(SCtl) <= 1024, "control block");
+// optional phase clocks (development builds, -DPOTUS_PROF): thread 0 accumulates cycles per phase of the sweep
+#ifdef POTUS_PROF
+#define SPROF_DECL long long sprof_t_ = clock64()
+#define SPROF(i) do { if (threadIdx.x == 0) { long long n_ = clock64(); SCTL().prof[i] += (unsigned long long)(n_ - sprof_t_); sprof_t_ = n_; } } while (0)
+#else
+#define SPROF_DECL
+#define SPROF(i)
+#endif
 
 __device__ __forceinline__ const ModelS& SMD() { return *SMP(const ModelS, SS_MODEL); }
 __device__ __forceinline__ SCtl& SCTL() { return *SMP(SCtl, SS_CTL); }
@@ -230,6 +241,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
   LeafAcc la{0.f, 0.f, 0.f};
   const int pr = tid & 127, qd = tid >> 7, c0 = 2 * pr;
   const bool colload = c0 < SP, colwrite = c0 < 16 * m.KS;
+  SPROF_DECL;
 
   // ---------------- stage the small parameter block; zero accumulators
   for (int i = tid; i < m.nzs; i += SNT) { qnz[i] = qin[oz + i]; gnz[i] = 0.f; }
@@ -311,6 +323,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
   }
   if (tid < 256) sF(SS_CZN)[tid] = 0.f;   // from here on: column sums of the position being written
   __syncthreads();
+  SPROF(0);
 
   // ================================================================ tiles of 128 days
   for (int tile = 0; tile < m.NTILE; ++tile) {
@@ -318,35 +331,49 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     const int p0 = __ldg(m.tile_ptr + tile), p1 = __ldg(m.tile_ptr + tile + 1);
     // ---------------- A: W tile -> fp16 hi/lo planes.  W[t] = a_T zT + a_w (colsum - sum_{u<t} Z[u])
     {
-      float2 ex[32];
+      // pass 1: day-quarter totals of the innovations (rows >= T-1 carry none)
       float r0 = 0.f, r1 = 0.f;
       const float* zp = qin + (size_t)(t0 + 32 * qd) * SP + c0;
+      const int nrow_z = min(32, max(0, T - 1 - (t0 + 32 * qd)));   // rows of this thread that hold a walk innovation
+      if (colload) {
 #pragma unroll
-      for (int d = 0; d < 32; ++d) {
-        float2 z = make_float2(0.f, 0.f);
-        if (colload && (t0 + 32 * qd + d) < T - 1) z = *reinterpret_cast<const float2*>(zp + (size_t)d * SP);
-        ex[d] = make_float2(r0, r1);
-        r0 += z.x; r1 += z.y;
+        for (int d0 = 0; d0 < 32; d0 += 8) {
+          float2 z[8];
+#pragma unroll
+          for (int d = 0; d < 8; ++d) z[d] = (d0 + d < nrow_z) ? *reinterpret_cast<const float2*>(zp + (size_t)(d0 + d) * SP) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) { r0 += z[d].x; r1 += z[d].y; }
+        }
       }
       *reinterpret_cast<float2*>(sF(SS_QTOT) + qd * 256 + c0) = make_float2(r0, r1);
       __syncthreads();
       float2 off = *reinterpret_cast<const float2*>(sF(SS_CARZ) + c0);
       for (int q2 = 0; q2 < qd; ++q2) { const float2 t2 = *reinterpret_cast<const float2*>(sF(SS_QTOT) + q2 * 256 + c0); off.x += t2.x; off.y += t2.y; }
       const float2 base = *reinterpret_cast<const float2*>(sF(SS_BASE) + c0);
+      // pass 2: the same rows again (L2 hits), running prefix, split, store
       if (colwrite) {
         unsigned char* ap = smem_raw + SS_A + (uint32_t)(c0 >> 3) * SA_LBO + (uint32_t)(c0 & 7) * 2 + (uint32_t)(4 * qd) * SA_SBO;
+        float e0 = off.x, e1 = off.y;   // sum of the innovations of all earlier days
+        const int nrow = min(32, max(0, T - (t0 + 32 * qd)));
 #pragma unroll
-        for (int d = 0; d < 32; ++d) {
-          float v0 = 0.f, v1 = 0.f;
-          if ((t0 + 32 * qd + d) < T) { v0 = fmaf(-m.a_w, off.x + ex[d].x, base.x); v1 = fmaf(-m.a_w, off.y + ex[d].y, base.y); }
-          if (c0 >= S) v0 = 0.f;
-          if (c0 + 1 >= S) v1 = 0.f;
-          const __half2 hi = __floats2half2_rn(v0, v1);
-          const float2 hf = __half22float2(hi);
-          const __half2 lo = __floats2half2_rn((v0 - hf.x) * 2048.0f, (v1 - hf.y) * 2048.0f);
-          const uint32_t o = (uint32_t)(d >> 3) * SA_SBO + (uint32_t)(d & 7) * 16;
-          *reinterpret_cast<__half2*>(ap + o) = hi;
-          *reinterpret_cast<__half2*>(ap + SA_PLANE + o) = lo;
+        for (int d0 = 0; d0 < 32; d0 += 8) {
+          float2 z[8];
+#pragma unroll
+          for (int d = 0; d < 8; ++d) z[d] = (colload && d0 + d < nrow_z) ? *reinterpret_cast<const float2*>(zp + (size_t)(d0 + d) * SP) : make_float2(0.f, 0.f);
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            float v0 = 0.f, v1 = 0.f;
+            if (d0 + d < nrow) { v0 = fmaf(-m.a_w, e0, base.x); v1 = fmaf(-m.a_w, e1, base.y); }
+            e0 += z[d].x; e1 += z[d].y;
+            if (c0 >= S) v0 = 0.f;
+            if (c0 + 1 >= S) v1 = 0.f;
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            const float2 hf = __half22float2(hi);
+            const __half2 lo = __floats2half2_rn((v0 - hf.x) * 2048.0f, (v1 - hf.y) * 2048.0f);
+            const uint32_t o = (uint32_t)((d0 + d) >> 3) * SA_SBO + (uint32_t)((d0 + d) & 7) * 16;
+            *reinterpret_cast<__half2*>(ap + o) = hi;
+            *reinterpret_cast<__half2*>(ap + SA_PLANE + o) = lo;
+          }
         }
       }
       ptx::fence_proxy_async_smem();
@@ -354,8 +381,10 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       __syncthreads();
       if (qd == 3) *reinterpret_cast<float2*>(sF(SS_CARZ) + c0) = make_float2(off.x + r0, off.y + r1);
     }
+    SPROF(1);
     // ---------------- B: mu_b^T = W^T X^T
     s_gemm(0, npre);
+    SPROF(2);
     // ---------------- C: mu_b tile (+ prior) and the national average of each day (stan:87)
     {
       const float part = s_epilogue(1.0f / 256.0f, sF(SS_PRIOR), 0.f, nullptr, sF(SS_W));
@@ -366,6 +395,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       npre = s_prefetch(1);
       __syncthreads();
     }
+    SPROF(3);
     // ---------------- optional outputs of this point (transformed parameters of the days of this tile)
     if (!LEAF) {
       const int nrow = min(ST_ROWS, T - t0);
@@ -384,39 +414,59 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     {
       const float* mu = sF(SS_A);
       const float nat_pb = ctl.nat_pb;
-      for (int k = p0 + tid; k < p1; k += SNT) {
-        const uint32_t w0 = __ldg(m.pw0 + k);
-        const int s = w0 & 511, dl = (w0 >> 9) & 127, mo = (w0 >> 16) & 7, po = (w0 >> 19) & 7;
-        const int p = __ldg(m.ppol + k);
-        const float x = qin[m.o_x + k];
-        const bool nat = (s == S);
-        const float sigx = nat ? m.sig_n : m.sig_s;
-        float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + p] + sigx * x;
-        if (m.full) {
-          eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
-          if ((w0 >> 22) & 1) eta += sF(SS_E)[t0 + dl];
-        }
-        float f, r;
-        s_poll_term(eta, __ldg(m.pn + k), __ldg(m.peh + k), __ldg(m.pph + k), __ldg(m.prh + k), f, r);
-        fsum += f;
-        rbuf[k] = r;
-        qsq = fmaf(x, x, qsq);
-        const float gx = x - sigx * r;
-        if (LEAF) {
-          const size_t e = (size_t)m.o_x + k;
-          float qn, pn, P;
-          s_leaf_elem(x, gx, io.ph[e], io.sm[e], odd ? io.Lr[e] : 0.f, odd, hs, eps_s, qn, pn, P, la);
-          io.qout[e] = qn; io.ph[e] = pn; io.Pdst[e] = P;
-        } else {
-          io.gout[(size_t)m.o_x + k] = gx;
-        }
-        if (m.full) {
+      float* rpol = rbuf + m.rp_off;
+      constexpr int UD = 4;   // polls per thread in flight: every global load of a batch is issued before the first use
+      for (int kb = p0 + tid; kb < p1; kb += UD * SNT) {
+        uint32_t w0[UD], pm[UD];
+        int pp[UD];
+        float x[UD], nn[UD], eh[UD], phh[UD], rh[UD], pv[UD], sv[UD], lrv[UD];
 #pragma unroll
-          for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
-          gm[MAX_MODE - 1] += r;
+        for (int u = 0; u < UD; ++u) {
+          const int k = kb + u * SNT;
+          if (k < p1) {
+            w0[u] = __ldg(m.pw0 + k); pp[u] = __ldg(m.ppol + k); pm[u] = __ldg(m.perm + k);
+            x[u] = qin[m.o_x + k];
+            nn[u] = __ldg(m.pn + k); eh[u] = __ldg(m.peh + k); phh[u] = __ldg(m.pph + k); rh[u] = __ldg(m.prh + k);
+            if (LEAF) { const size_t e = (size_t)m.o_x + k; pv[u] = io.ph[e]; sv[u] = io.sm[e]; lrv[u] = odd ? io.Lr[e] : 0.f; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UD; ++u) {
+          const int k = kb + u * SNT;
+          if (k < p1) {
+            const int s = w0[u] & 511, dl = (w0[u] >> 9) & 127, mo = (w0[u] >> 16) & 7, po = (w0[u] >> 19) & 7;
+            const bool nat = (s == S);
+            const float sigx = nat ? m.sig_n : m.sig_s;
+            float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp[u]] + sigx * x[u];
+            if (m.full) {
+              eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
+              if ((w0[u] >> 22) & 1) eta += sF(SS_E)[t0 + dl];
+            }
+            float f, r;
+            s_poll_term(eta, nn[u], eh[u], phh[u], rh[u], f, r);
+            fsum += f;
+            rbuf[k] = r;
+            rpol[pm[u]] = r;
+            qsq = fmaf(x[u], x[u], qsq);
+            const float gx = x[u] - sigx * r;
+            if (LEAF) {
+              const size_t e = (size_t)m.o_x + k;
+              float qn, pn, P;
+              s_leaf_elem(x[u], gx, pv[u], sv[u], lrv[u], odd, hs, eps_s, qn, pn, P, la);
+              io.qout[e] = qn; io.ph[e] = pn; io.Pdst[e] = P;
+            } else {
+              io.gout[(size_t)m.o_x + k] = gx;
+            }
+            if (m.full) {
+#pragma unroll
+              for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
+              gm[MAX_MODE - 1] += r;
+            }
+          }
         }
       }
     }
+    SPROF(4);
     __syncthreads();
     // ---------------- E1: clear the operand planes (the mu_b tile is dead)
     {
@@ -425,33 +475,56 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       for (int i = tid; i < (int)(2 * SA_PLANE / 16); i += SNT) a4[i] = z;
     }
     __syncthreads();
+    SPROF(5);
     // ---------------- E2: G operand cells = sums of residuals per (state, day); per-day sums for e_bias / national
     {
-      for (int k = p0 + tid; k < p1; k += SNT) {
-        const uint32_t key = __ldg(m.pw0 + k) & 0xffffu;
-        const uint32_t prev = (k > p0) ? (__ldg(m.pw0 + k - 1) & 0xffffu) : 0xffffffffu;
-        const int s = key & 511;
-        if (key != prev && s < S) {
-          float acc = rbuf[k];
-          for (int j = k + 1; j < p1 && (__ldg(m.pw0 + j) & 0xffffu) == key; ++j) acc += rbuf[j];
-          const int dl = key >> 9;
-          __half hi, lo;
-          ptx::split_f16(acc * m.scale_G, hi, lo);
-          const uint32_t o = (uint32_t)(s >> 3) * SA_LBO + (uint32_t)(dl >> 3) * SA_SBO + (uint32_t)(dl & 7) * 16 + (uint32_t)(s & 7) * 2;
-          *reinterpret_cast<__half*>(smem_raw + SS_A + o) = hi;
-          *reinterpret_cast<__half*>(smem_raw + SS_A + SA_PLANE + o) = lo;
+      constexpr int UC = 4;
+      for (int kb = p0 + tid; kb < p1; kb += UC * SNT) {
+        uint32_t key[UC], prev[UC], next[UC];
+        float rr[UC];
+#pragma unroll
+        for (int u = 0; u < UC; ++u) {
+          const int k = kb + u * SNT;
+          key[u] = 0xffffffffu; prev[u] = 0xffffffffu; next[u] = 0xfffffffeu; rr[u] = 0.f;
+          if (k < p1) {
+            key[u] = __ldg(m.pw0 + k) & 0xffffu;
+            if (k > p0) prev[u] = __ldg(m.pw0 + k - 1) & 0xffffu;
+            if (k + 1 < p1) next[u] = __ldg(m.pw0 + k + 1) & 0xffffu;
+            rr[u] = rbuf[k];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < UC; ++u) {
+          const int k = kb + u * SNT;
+          const int s = key[u] & 511;
+          if (k < p1 && key[u] != prev[u] && s < S) {   // head of a (state, day) run
+            float acc = rr[u];
+            if (next[u] == key[u]) {   // (runs longer than one poll are the exception)
+              acc += rbuf[k + 1];
+              for (int j = k + 2; j < p1 && (__ldg(m.pw0 + j) & 0xffffu) == key[u]; ++j) acc += rbuf[j];
+            }
+            const int dl = key[u] >> 9;
+            __half hi, lo;
+            ptx::split_f16(acc * m.scale_G, hi, lo);
+            const uint32_t o = (uint32_t)(s >> 3) * SA_LBO + (uint32_t)(dl >> 3) * SA_SBO + (uint32_t)(dl & 7) * 16 + (uint32_t)(s & 7) * 2;
+            *reinterpret_cast<__half*>(smem_raw + SS_A + o) = hi;
+            *reinterpret_cast<__half*>(smem_raw + SS_A + SA_PLANE + o) = lo;
+          }
         }
       }
-      for (int dl = w; dl < ST_ROWS; dl += 16) {   // one warp per day, lanes stride over the day's polls (fixed order)
+      SPROF(6);
+      for (int dl = w; dl < ST_ROWS; dl += 16) {   // per-day sums: one warp per day, lanes stride over its polls (fixed order)
         const int t = t0 + dl;
         float ae = 0.f, an = 0.f;
         if (t < T) {
           const int k0 = __ldg(m.day_ptr + t), k1 = __ldg(m.day_ptr + t + 1);
-          for (int k = k0 + l; k < k1; k += 32) {
-            const uint32_t w0 = __ldg(m.pw0 + k);
-            const float r = rbuf[k];
-            if ((w0 >> 22) & 1) ae += r;
-            if ((int)(w0 & 511) == S) an += r;
+          for (int kb = k0 + l; kb < k1; kb += 8 * 32) {
+            uint32_t w8[8];
+            float r8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int k = kb + 32 * u; w8[u] = 0u; r8[u] = 0.f; if (k < k1) { w8[u] = __ldg(m.pw0 + k); r8[u] = rbuf[k]; } }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { if ((w8[u] >> 22) & 1) ae += r8[u]; if ((int)(w8[u] & 511) == S) an += r8[u]; }
           }
         }
 #pragma unroll
@@ -459,11 +532,13 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
         if (l == 0) { sF(SS_RND)[dl] = an; if (t < T) sF(SS_GE)[t] = ae; }
       }
     }
+    SPROF(7);
     ptx::fence_proxy_async_smem();
     ptx::tc_fence_before();
     __syncthreads();
     // ---------------- F: H^T = G^T X
     s_gemm(1, npre);
+    SPROF(8);
     // ---------------- G: H tile; the national polls enter as the rank-1 term  rn_day[t] * (L0^T w)
     {
       const int row = 32 * (w & 3) + l;
@@ -472,6 +547,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       if (tid == 0) ctl.gemm_cnt++;
       npre = (tile + 1 < m.NTILE) ? s_prefetch(0) : 0;
     }
+    SPROF(9);
     // ---------------- H: prefix of H over days -> gradient of the walk block -> leapfrog tail
     {
       const float* hp = sF(SS_A) + (32 * qd) * pitch + c0;
@@ -527,6 +603,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     }
   }
   // ================================================================ after the last tile
+  SPROF(10);
   // class sums of residuals (mode / population), fixed shuffle trees
   if (m.full) {
 #pragma unroll
@@ -543,15 +620,15 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       for (int j = 0; j < MAX_MODE; ++j) { red[j] = (double)gm[j]; red[4 + j] = (double)gp[j]; }
     }
   }
-  // pollster sums, level 1: one warp per segment task, lanes stride over the id list
-  for (int tk = w; tk < m.n_ptask; tk += 16) {
-    const uint32_t st = __ldg(m.ptask + tk);
-    const int cnt = __ldg(m.ptask_cnt + tk);
-    float acc = 0.f;
-    for (int j = l; j < cnt; j += 32) acc += rbuf[__ldg(m.pol_ids + st + j)];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (l == 0) sF(SS_PSUM)[tk] = acc;
+  // pollster sums, level 1: one thread per 16-residual segment of the pollster-grouped copy (pads are zero), fixed order
+  {
+    const float* rpol = rbuf + m.rp_off;
+    float* psum = sF(SS_A);   // the tile region is free after the last tile
+    for (int sg = tid; sg < m.n_seg; sg += SNT) {
+      const float4* v = reinterpret_cast<const float4*>(rpol + (size_t)sg * ST_SEGL);
+      const float4 a = v[0], b = v[1], c = v[2], d = v[3];
+      psum[sg] = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) + (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    }
   }
   if (tid < S) {   // raw_mu_b_T and raw_polling_bias: both driven by sum_t H[:,t] = L0^T g_pb
     const float h = sF(SS_CARH)[tid];
@@ -559,11 +636,13 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     gnz[(m.o_zb - oz) + tid] = m.a_b * h;
   }
   __syncthreads();
-  for (int p = tid; p < m.P; p += SNT) {
-    const int a = __ldg(m.pol_tptr + p), b = __ldg(m.pol_tptr + p + 1);
+  for (int p = w; p < m.P; p += 16) {   // level 2: one warp per pollster over its segment sums
+    const int a = __ldg(m.seg_ptr + p), b = __ldg(m.seg_ptr + p + 1);
     float acc = 0.f;
-    for (int j = a; j < b; ++j) acc += sF(SS_PSUM)[j];
-    gnz[(m.o_c - oz) + p] = m.sig_c * acc;
+    for (int j = a + l; j < b; j += 32) acc += sF(SS_A)[j];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (l == 0) gnz[(m.o_c - oz) + p] = m.sig_c * acc;
   }
   if (m.full && w == 2 && l < 2 * MAX_MODE) {
     const int j = l % MAX_MODE;
@@ -671,6 +750,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     io.kk = (float)tot[1]; io.c1a = (float)tot[2]; io.c1b = (float)tot[3];
     __syncthreads();
   }
+  SPROF(11);
 }
 
 __device__ __noinline__ void s_eval(SweepIO& io, float* rbuf) { s_sweep_body<false>(io, rbuf); }
@@ -709,9 +789,24 @@ __device__ __forceinline__ void s_block_sum(float (&v)[N]) {
   }
 }
 
+// (every vector length is a multiple of 4 * SNT float4s: loops are unrolled so that all loads of a batch are in flight together)
 __device__ __forceinline__ void s_copy(float* dst, const float* src) {
   const int n = nv4();
-  for (int i = threadIdx.x; i < n; i += SNT) st4(dst, i, ld4(src, i));
+  for (int i = threadIdx.x; i < n; i += 4 * SNT) {
+    const float4 a = ld4(src, i), b = ld4(src, i + SNT), c = ld4(src, i + 2 * SNT), d = ld4(src, i + 3 * SNT);
+    st4(dst, i, a); st4(dst, i + SNT, b); st4(dst, i + 2 * SNT, c); st4(dst, i + 3 * SNT, d);
+  }
+}
+// dst = a + b
+__device__ __forceinline__ void s_add(float* dst, const float* a, const float* b) {
+  const int n = nv4();
+  for (int i = threadIdx.x; i < n; i += 4 * SNT) {
+    float4 x[4], y[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { x[u] = ld4(a, i + u * SNT); y[u] = ld4(b, i + u * SNT); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st4(dst, i + u * SNT, make_float4(x[u].x + y[u].x, x[u].y + y[u].y, x[u].z + y[u].z, x[u].w + y[u].w));
+  }
 }
 
 // fresh whitened momentum P ~ N(0, I) on the valid slots; returns |P|^2 (block total)
@@ -735,25 +830,36 @@ __device__ __forceinline__ bool s_merge(const float* Lb, const float* Le, const 
                                         float* S_out) {
   const int n = nv4();
   float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < n; i += SNT) {
-    const float4 lb4 = ld4(Lb, i), le4 = ld4(Le, i), p4 = ld4(P, i);
-    const float4 lr4 = Lr ? ld4(Lr, i) : make_float4(lb4.x + le4.x, lb4.y + le4.y, lb4.z + le4.z, lb4.w + le4.w);
-    const float4 s4 = S_in ? ld4(S_in, i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 rb4 = Rb ? ld4(Rb, i) : p4;
-    const float lb[4] = {lb4.x, lb4.y, lb4.z, lb4.w}, le[4] = {le4.x, le4.y, le4.z, le4.w}, p[4] = {p4.x, p4.y, p4.z, p4.w};
-    const float lr[4] = {lr4.x, lr4.y, lr4.z, lr4.w}, rb[4] = {rb4.x, rb4.y, rb4.z, rb4.w};
-    float s[4] = {s4.x, s4.y, s4.z, s4.w};
+  for (int i0 = threadIdx.x; i0 < n; i0 += 2 * SNT) {
+    float4 lb4[2], le4[2], p4[2], lr4[2], s4[2], rb4[2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float x = lr[j] + s[j] + p[j];
-      v[0] = fmaf(lb[j], x, v[0]); v[1] = fmaf(p[j], x, v[1]);
-      const float y = lr[j] + rb[j];
-      v[2] = fmaf(lb[j], y, v[2]); v[3] = fmaf(rb[j], y, v[3]);
-      const float z = s[j] + p[j] + le[j];
-      v[4] = fmaf(le[j], z, v[4]); v[5] = fmaf(p[j], z, v[5]);
-      s[j] += lr[j];
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * SNT;
+      lb4[u] = ld4(Lb, i); le4[u] = ld4(Le, i); p4[u] = ld4(P, i);
+      if (Lr) lr4[u] = ld4(Lr, i);
+      s4[u] = S_in ? ld4(S_in, i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (Rb) rb4[u] = ld4(Rb, i);
     }
-    st4(S_out, i, make_float4(s[0], s[1], s[2], s[3]));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + u * SNT;
+      if (!Lr) lr4[u] = make_float4(lb4[u].x + le4[u].x, lb4[u].y + le4[u].y, lb4[u].z + le4[u].z, lb4[u].w + le4[u].w);
+      if (!Rb) rb4[u] = p4[u];
+      const float lb[4] = {lb4[u].x, lb4[u].y, lb4[u].z, lb4[u].w}, le[4] = {le4[u].x, le4[u].y, le4[u].z, le4[u].w}, p[4] = {p4[u].x, p4[u].y, p4[u].z, p4[u].w};
+      const float lr[4] = {lr4[u].x, lr4[u].y, lr4[u].z, lr4[u].w}, rb[4] = {rb4[u].x, rb4[u].y, rb4[u].z, rb4[u].w};
+      float sv[4] = {s4[u].x, s4[u].y, s4[u].z, s4[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = lr[j] + sv[j] + p[j];
+        v[0] = fmaf(lb[j], x, v[0]); v[1] = fmaf(p[j], x, v[1]);
+        const float y = lr[j] + rb[j];
+        v[2] = fmaf(lb[j], y, v[2]); v[3] = fmaf(rb[j], y, v[3]);
+        const float z = sv[j] + p[j] + le[j];
+        v[4] = fmaf(le[j], z, v[4]); v[5] = fmaf(p[j], z, v[5]);
+        sv[j] += lr[j];
+      }
+      st4(S_out, i, make_float4(sv[0], sv[1], sv[2], sv[3]));
+    }
   }
   s_block_sum(v);
   return v[0] > 0.f && v[1] > 0.f && v[2] > 0.f && v[3] > 0.f && v[4] > 0.f && v[5] > 0.f;
@@ -787,22 +893,30 @@ __device__ __noinline__ void s_transition(const SRunArgs& a, float* ws, float* r
   {
     const float hs = 0.5f * eps;
     float *tbb = s_slot(ws, SW_TOP_BB), *tff = s_slot(ws, SW_TOP_FF), *trho = s_slot(ws, SW_TOP_RHO), *ca = s_slot(ws, SW_CAND_A);
-    for (int i = tid; i < n4; i += SNT) {
-      const float4 P = ld4(P0, i), s = ld4(sm, i), g = ld4(G, i), q = ld4(qcur, i);
-      const float Pv[4] = {P.x, P.y, P.z, P.w}, sv[4] = {s.x, s.y, s.z, s.w}, gv[4] = {g.x, g.y, g.z, g.w}, qv[4] = {q.x, q.y, q.z, q.w};
-      float pf[4], pb[4], qf[4], qb[4];
+    for (int i0 = tid; i0 < n4; i0 += 2 * SNT) {
+      float4 P2[2], s2[2], g2[2], q2[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        pf[j] = fmaf(-hs * sv[j], gv[j], Pv[j]);
-        pb[j] = fmaf(hs * sv[j], gv[j], Pv[j]);
-        qf[j] = fmaf(eps * sv[j], pf[j], qv[j]);
-        qb[j] = fmaf(-eps * sv[j], pb[j], qv[j]);
+      for (int u = 0; u < 2; ++u) { const int i = i0 + u * SNT; P2[u] = ld4(P0, i); s2[u] = ld4(sm, i); g2[u] = ld4(G, i); q2[u] = ld4(qcur, i); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * SNT;
+        const float4 P = P2[u], q = q2[u];
+        const float Pv[4] = {P.x, P.y, P.z, P.w}, sv[4] = {s2[u].x, s2[u].y, s2[u].z, s2[u].w}, gv[4] = {g2[u].x, g2[u].y, g2[u].z, g2[u].w},
+                    qv[4] = {q.x, q.y, q.z, q.w};
+        float pf[4], pb[4], qf[4], qb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          pf[j] = fmaf(-hs * sv[j], gv[j], Pv[j]);
+          pb[j] = fmaf(hs * sv[j], gv[j], Pv[j]);
+          qf[j] = fmaf(eps * sv[j], pf[j], qv[j]);
+          qb[j] = fmaf(-eps * sv[j], pb[j], qv[j]);
+        }
+        st4(endp[1], i, make_float4(pf[0], pf[1], pf[2], pf[3]));
+        st4(endp[0], i, make_float4(pb[0], pb[1], pb[2], pb[3]));
+        st4(endq[1][0], i, make_float4(qf[0], qf[1], qf[2], qf[3]));
+        st4(endq[0][0], i, make_float4(qb[0], qb[1], qb[2], qb[3]));
+        st4(tbb, i, P); st4(tff, i, P); st4(trho, i, P); st4(ca, i, q);
       }
-      st4(endp[1], i, make_float4(pf[0], pf[1], pf[2], pf[3]));
-      st4(endp[0], i, make_float4(pb[0], pb[1], pb[2], pb[3]));
-      st4(endq[1][0], i, make_float4(qf[0], qf[1], qf[2], qf[3]));
-      st4(endq[0][0], i, make_float4(qb[0], qb[1], qb[2], qb[3]));
-      st4(tbb, i, P); st4(tff, i, P); st4(trho, i, P); st4(ca, i, q);
     }
   }
   int samp = SW_CAND_A, prop = SW_CAND_B;
@@ -839,6 +953,7 @@ __device__ __noinline__ void s_transition(const SRunArgs& a, float* ws, float* r
       SweepIO io{};
       io.qin = qi; io.qout = qo; io.ph = endp[di]; io.sm = sm; io.Pdst = Pd; io.Lr = (t > 0) ? first_slot(n - 1) : nullptr; io.eps_s = eps_s;
       s_leaf(io, rbuf);
+      SPROF_DECL;
       double h = ctl.U + 0.5 * (double)io.kk;
       if (!(h == h)) h = CUDART_INF;
       ++n_leap;
@@ -856,16 +971,17 @@ __device__ __noinline__ void s_transition(const SRunArgs& a, float* ws, float* r
           if (tid == 0) { ctl.U_prop = ctl.U; ctl.H_prop = h; }
         }
       }
+      SPROF(12);
       // U-turn checks for every subtree this leaf completes (level 0 came with the sweep)
       if (t > 0) ok = (io.c1a > 0.f) && (io.c1b > 0.f);
       if (t > 1 && ok) ok = s_merge(first_slot(n - 3), s_slot(ws, SW_LEFT_E), nullptr, first_slot(n - 1), Pd, first_slot(n - 1), SR);
       for (int k = 2; k < t && ok; ++k)
         ok = s_merge(first_slot(n - (2 << k) + 1), s_slot(ws, SW_LEFT_E + k - 1), s_slot(ws, SW_LEFT_R + k - 1), first_slot(n - (1 << k) + 1), Pd, SR, SR);
       if (!ok) break;
+      SPROF(13);
       if (!last) {
         if (t >= 2) {   // stored left half at level t: e = P (already there), r = S + P
-          float* r = s_slot(ws, SW_LEFT_R + t - 1);
-          for (int i = tid; i < n4; i += SNT) { const float4 p = ld4(Pd, i), s = ld4(SR, i); st4(r, i, make_float4(s.x + p.x, s.y + p.y, s.z + p.z, s.w + p.w)); }
+          s_add(s_slot(ws, SW_LEFT_R + t - 1), SR, Pd);
         }
       } else {
         // last leaf: merge the finished subtree with the existing trajectory (top level of base_nuts::transition)
@@ -877,13 +993,14 @@ __device__ __noinline__ void s_transition(const SRunArgs& a, float* ws, float* r
         persist = s_merge(F, A, s_slot(ws, SW_TOP_RHO), Rb, Pd, Sin, SR);
         float* rho = s_slot(ws, SW_TOP_RHO);
         float* end = s_slot(ws, dir > 0 ? SW_TOP_FF : SW_TOP_BB);
-        for (int i = tid; i < n4; i += SNT) {
-          const float4 p = ld4(Pd, i), s = ld4(SR, i);
-          st4(rho, i, make_float4(s.x + p.x, s.y + p.y, s.z + p.z, s.w + p.w));
-          st4(end, i, p);
-        }
+        s_add(rho, SR, Pd);
+        s_copy(end, Pd);
       }
       __syncthreads();
+      SPROF(14);
+#ifdef POTUS_PROF
+      if (tid == 0) ctl.prof[31] += 1;
+#endif
     }
     if (!ok) break;
     ++depth;
@@ -988,7 +1105,7 @@ __device__ __forceinline__ void s_cta_teardown() {
 // test hook: log density + gradient for n positions (potus_logp_grad on shapes the resident kernel does not hold)
 extern "C" __global__ void __launch_bounds__(SNT, 1) potus_stream_eval_kernel(const __grid_constant__ SEvalArgs a) {
   s_cta_setup(a.m);
-  float* rbuf = a.rbuf + (size_t)blockIdx.x * ((a.m.N + 3) & ~3);
+  float* rbuf = a.rbuf + (size_t)blockIdx.x * a.m.rb_len;
   for (int i = blockIdx.x; i < a.n; i += gridDim.x) {
     SweepIO io{};
     io.qin = a.q_in + (size_t)i * a.m.VL;
@@ -1007,9 +1124,12 @@ extern "C" __global__ void __launch_bounds__(SNT, 1) potus_stream_kernel(const _
   const int tid = threadIdx.x;
   const int VL = m.VL, n4 = VL >> 2;
   float* ws = a.workspace + (size_t)blockIdx.x * SW_NSLOT * VL;
-  float* rbuf = a.rbuf + (size_t)blockIdx.x * ((m.N + 3) & ~3);
+  float* rbuf = a.rbuf + (size_t)blockIdx.x * m.rb_len;
   const int n_iter_total = a.iter_warmup + a.iter_sampling;
   const SEmit none{nullptr, nullptr};
+#ifdef POTUS_PROF
+  if (tid < 32) ctl.prof[tid] = 0ull;
+#endif
 
   for (;;) {
     __syncthreads();
@@ -1164,6 +1284,9 @@ extern "C" __global__ void __launch_bounds__(SNT, 1) potus_stream_kernel(const _
     if (tid == 0) { ctl.cs.iter = a.iter_end; a.cs[chain] = ctl.cs; }
     __syncthreads();
   }
+#ifdef POTUS_PROF
+  if (a.prof != nullptr && tid < 32) atomicAdd(a.prof + tid, ctl.prof[tid]);
+#endif
   s_cta_teardown();
 }
 

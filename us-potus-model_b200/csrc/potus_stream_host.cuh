@@ -178,30 +178,24 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
     for (int k = 0; k <= s; ++k) l0t[(size_t)k * m.SP + s] = (float)L0[(size_t)s * S + k];
   }
 
-  // ---- pollster segment-sum tasks over the sorted polls
+  // ---- pollster sums: a second copy of the residuals grouped by pollster (each pollster padded to ST_SEGL entries, pads stay 0)
   std::vector<std::vector<uint32_t>> byp(P);
   for (int k = 0; k < N; ++k) byp[hp[k].p].push_back((uint32_t)k);
-  int CH = 128;
-  for (;;) {
-    long nt = 0;
-    for (int p = 0; p < P; ++p) nt += ((long)byp[p].size() + CH - 1) / CH;
-    if (nt <= ST_PTASK_CAP) break;
-    CH *= 2;
-    if (CH > 32768) return fail(POTUS_ERR_UNSUPPORTED, "too many polls per pollster for the segment-sum task table");
-  }
-  std::vector<uint32_t> pol_ids, ptask;
-  std::vector<uint16_t> ptask_cnt;
-  std::vector<int32_t> pol_tptr(P + 1, 0);
-  for (int p = 0; p < P; ++p) {
-    const uint32_t st = (uint32_t)pol_ids.size();
-    pol_ids.insert(pol_ids.end(), byp[p].begin(), byp[p].end());
-    for (size_t a = 0; a < byp[p].size(); a += CH) {
-      ptask.push_back(st + (uint32_t)a);
-      ptask_cnt.push_back((uint16_t)std::min<size_t>(CH, byp[p].size() - a));
+  std::vector<uint32_t> perm(N, 0);
+  std::vector<int32_t> seg_ptr(P + 1, 0);
+  {
+    uint32_t pos = 0;
+    for (int p = 0; p < P; ++p) {
+      for (size_t a = 0; a < byp[p].size(); ++a) perm[byp[p][a]] = pos + (uint32_t)a;
+      const uint32_t nseg = (uint32_t)((byp[p].size() + ST_SEGL - 1) / ST_SEGL);
+      pos += nseg * ST_SEGL;
+      seg_ptr[p + 1] = seg_ptr[p] + (int32_t)nseg;
     }
-    pol_tptr[p + 1] = (int32_t)ptask.size();
+    m.n_seg = seg_ptr[P];
+    m.rp_off = (N + 3) & ~3;
+    m.rb_len = m.rp_off + (int)pos + 4;
+    if ((size_t)m.n_seg * 4 > SA_REGION) return fail(POTUS_ERR_UNSUPPORTED, "too many pollster segments for the shared-memory partial-sum table");
   }
-  m.n_ptask = (int)ptask.size();
 
   // ---- vector slot -> Stan unconstrained index
   sh.map_i2s.assign(m.VL, -1);
@@ -239,10 +233,8 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
   if ((rc = upload_to(al, prh, &p))) return rc; m.prh = (const float*)p;
   if ((rc = upload_to(al, tile_ptr, &p))) return rc; m.tile_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, day_ptr, &p))) return rc; m.day_ptr = (const int32_t*)p;
-  if ((rc = upload_to(al, pol_ids, &p))) return rc; m.pol_ids = (const uint32_t*)p;
-  if ((rc = upload_to(al, ptask, &p))) return rc; m.ptask = (const uint32_t*)p;
-  if ((rc = upload_to(al, ptask_cnt, &p))) return rc; m.ptask_cnt = (const uint16_t*)p;
-  if ((rc = upload_to(al, pol_tptr, &p))) return rc; m.pol_tptr = (const int32_t*)p;
+  if ((rc = upload_to(al, perm, &p))) return rc; m.perm = (const uint32_t*)p;
+  if ((rc = upload_to(al, seg_ptr, &p))) return rc; m.seg_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, sh.map_i2s, &p))) return rc; m.map_i2s = (const int32_t*)p;
   return POTUS_OK;
 }

@@ -16,9 +16,9 @@ constexpr int ST_MAXT = 512;             // days <= 512 (AR(1) vectors in shared
 constexpr int ST_MAXTILE = ST_MAXT / ST_ROWS;
 constexpr int ST_NZS_CAP = 2048;         // "small" non-walk parameters staged in shared memory: zT, zb, c, m, pop, u_mu, u_rho, ze
 constexpr int ST_NSTAGE = 3;             // B-operand ring (one MMA K-step of 16 per stage)
-constexpr int ST_PTASK_CAP = 1024;       // pollster segment-sum tasks
+constexpr int ST_SEGL = 16;              // residuals per pollster segment (level 1 of the pollster sums)
 constexpr int ST_MAXP = 1024;
-constexpr int ST_VCHUNK = SNT * 4;       // vectors are padded to a multiple of this (uniform float4 loops)
+constexpr int ST_VCHUNK = SNT * 4 * 4;   // vectors are padded to a multiple of this (uniform float4 loops, unrolled by up to 4)
 
 // ---- UMMA operand geometry (K-major, SWIZZLE_NONE, fp16 hi/lo planes).  A: 128 rows x 256 k.
 constexpr uint32_t SA_SBO = 128;                    // 8-row groups contiguous
@@ -48,8 +48,7 @@ constexpr uint32_t SS_QTOT = SS_CZN + 1024;                    // float [4][256]
 constexpr uint32_t SS_NATP = SS_QTOT + 4096;                   // float [4][128] partial national averages
 constexpr uint32_t SS_NAT = SS_NATP + 2048;                    // float [128]
 constexpr uint32_t SS_RND = SS_NAT + 512;                      // float [128] national residual per day of the tile
-constexpr uint32_t SS_PSUM = SS_RND + 512;                     // float [ST_PTASK_CAP]
-constexpr uint32_t SS_RED = SS_PSUM + ST_PTASK_CAP * 4;        // double [16][16]
+constexpr uint32_t SS_RED = SS_RND + 512;                      // double [16][16]
 constexpr uint32_t SS_CTL = SS_RED + 16 * 16 * 8;              // control block, 1024 B
 constexpr uint32_t SS_MODEL = SS_CTL + 1024;                   // ModelS copy, 1024 B
 constexpr uint32_t SS_TOTAL = SS_MODEL + 1024;
@@ -79,7 +78,7 @@ struct ModelS {
   int S, T, P, M, Pop, Nn, Ns, N, full, D;
   int SP, NP, KS, NTILE, VL;
   int o_zT, o_zb, o_c, o_m, o_pop, o_umu, o_urho, o_ze, o_x, nzs;   // o_* are offsets in the vector; small block = [o_zT, o_zT + nzs)
-  int n_ptask;
+  int n_seg, rp_off, rb_len;   // pollster segments; offset of the pollster-grouped residual copy in a CTA's residual buffer; its length
   float a_b, a_T, a_w, sig_c, sig_m, sig_pop, sig_n, sig_s, sig_e;
   float scale_G, inv_scale_G;
   double lp_const;
@@ -100,10 +99,8 @@ struct ModelS {
   const float* prh;
   const int32_t* tile_ptr;     // [NTILE+1] poll range of each tile
   const int32_t* day_ptr;      // [T+1]
-  const uint32_t* pol_ids;     // poll ids grouped by pollster
-  const uint32_t* ptask;       // [n_ptask] start (into pol_ids)
-  const uint16_t* ptask_cnt;   // [n_ptask]
-  const int32_t* pol_tptr;     // [P+1] task range of each pollster
+  const uint32_t* perm;        // [N] position of sorted poll k in the pollster-grouped residual copy (each pollster padded to ST_SEGL)
+  const int32_t* seg_ptr;      // [P+1] segment range of each pollster
   const int32_t* map_i2s;      // [VL] vector slot -> Stan unconstrained index (-1 = padding)
 };
 static_assert(sizeof(ModelS) <= 1024, "ModelS must fit its shared-memory slot");
@@ -118,11 +115,12 @@ struct SRunArgs {
   float* q; float* sqrt_m; float* wf_mean; float* wf_m2;   // per-chain persistent vectors [n_chains][VL]
   ChainState* cs;
   float* workspace;      // [gridDim.x][SW_NSLOT][VL]
-  float* rbuf;           // [gridDim.x][N rounded up] residuals of the current sweep
+  float* rbuf;           // [gridDim.x][m.rb_len] residuals of the current sweep (sorted order, then pollster-grouped)
   int* queue;
   float* draws;          // [n_chains*keep_per_chain][draw_len]
   float* monitor;        // [n_chains][iter_sampling][S+1]
   float* sampler_params; // [n_chains][iter_warmup+iter_sampling][8]
+  unsigned long long* prof; // optional [64] phase cycle counters (POTUS_PROF builds only)
 };
 
 struct SEvalArgs {       // test hook: lp/grad for n vectors
@@ -131,7 +129,7 @@ struct SEvalArgs {       // test hook: lp/grad for n vectors
   const float* q_in;     // [n][VL]
   float* g_out;          // [n][VL] gradient of U
   double* u_out;         // [n]
-  float* rbuf;           // [gridDim.x][N rounded up]
+  float* rbuf;           // [gridDim.x][m.rb_len]
 };
 
 }  // namespace potus

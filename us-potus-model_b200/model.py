@@ -144,9 +144,10 @@ class CmdStanModelB200:
     def sample(self, data: dict, seed: int = 1843, chains: int = 4, parallel_chains: int | None = None,
                iter_warmup: int = 500, iter_sampling: int = 500, refresh: int | None = None,
                adapt_delta: float = 0.8, max_treedepth: int = 10, keep_per_chain: int = 0, device: int = 0,
-               chain_id_offset: int = 0, init: float = 2.0, force_stream: bool = False) -> PotusFit:
+               chain_id_offset: int = 0, init: float = 2.0, force_stream: bool = False, n_gpus: int = 1) -> PotusFit:
         """cmdstanr `$sample()` argument names; `parallel_chains`/`refresh` are accepted and ignored
-        (all chains run concurrently on the GPU)."""
+        (all chains run concurrently on the GPU).  n_gpus > 1: the library itself shards `chains` over that many devices
+        in this one process and all-gathers the kept draws with NCCL (include/potus_b200.h, PotusConfig.n_gpus)."""
         lib = cabi.load_library()
         has_mode = "poll_mode_state" in data
         variant = self.variant or ("full" if has_mode else "no_mode")
@@ -157,7 +158,7 @@ class CmdStanModelB200:
         pd, keep = cabi.marshal_data(data)
         cfg = cabi.make_config(chains=chains, iter_warmup=iter_warmup, iter_sampling=iter_sampling, seed=seed,
                                keep_per_chain=keep_per_chain, max_treedepth=max_treedepth, adapt_delta=adapt_delta,
-                               init_radius=init, device=device, chain_id_offset=chain_id_offset, force_stream=force_stream)
+                               init_radius=init, device=device, chain_id_offset=chain_id_offset, force_stream=force_stream, n_gpus=n_gpus)
         h = C.c_void_p()
         cabi.check(lib, lib.potus_create(C.byref(pd), C.byref(cfg), C.byref(h)))
         try:
