@@ -115,6 +115,10 @@ typedef struct PotusSampler PotusSampler;
 POTUS_API int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
 /* Run warm-up + sampling for all chains; blocks until done. */
 POTUS_API int potus_run(PotusSampler* s);
+/* Optional, before potus_run, with iter_warmup == 0: start every chain from a given adapted state (resume / continue a run,
+ * or seed the sampling phase from another sampler's warm-up) instead of Stan's random inits + warm-up.
+ * theta [chains][D] row-major, Stan unconstrained order; stepsize [chains]; inv_metric [chains][D] (diagonal of M^-1). */
+POTUS_API int potus_set_state(PotusSampler* s, const double* theta, const double* stepsize, const double* inv_metric);
 /* Number of doubles potus_get_draws would write for `par` (0 if unknown). */
 POTUS_API size_t potus_draws_size(const PotusSampler* s, const char* par);
 /* Copy kept draws of one quantity to host, shaped like rstan::extract(out, pars=par)[[1]]:
@@ -129,6 +133,15 @@ POTUS_API size_t potus_draws_size(const PotusSampler* s, const char* par);
  *        under "# Diagonal elements of inverse mass matrix:"), Stan unconstrained order               */
 POTUS_API int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n);
 POTUS_API int potus_get_stats(PotusSampler* s, PotusStats* stats);
+/* On-device post-processing over ALL chains x iter_sampling monitored draws -- what the reference's reports compute on the host from
+ * rstan::extract(out, "predicted_score") (README.Rmd:206-300, final_2016.R:708-823), done where the draws are:
+ *   ev [S] electoral votes or NULL; ev_threshold (270);
+ *   state_table [(S+2)][8] row-major: mean, sd, 2.5%, 5%, 50%, 95%, 97.5% quantiles (exact order statistics, linear interpolation as
+ *     numpy / R type 7), P(> 0.5) of inv_logit(mu_b[s,T]); row S = national vote (state_weights-weighted mean of the shares of each draw);
+ *     row S+1 = democratic electoral votes of each draw, last column P(ev >= ev_threshold) (zeros when ev is NULL);
+ *   ess_table [(S+1)][3] row-major or NULL: Stan effective sample size, split R-hat and mean of the monitored scalars on the logit scale
+ *     (row S = national_mu_b_average[T]). */
+POTUS_API int potus_postprocess(PotusSampler* s, const double* ev, double ev_threshold, double* state_table, double* ess_table);
 /* Device pointers to the raw fp32 buffers (for the torch.distributed all-gather in bench.py; with n_gpus > 1, which = 0
  * is the all-gathered buffer on the first device, [n_gpus][ceil(chains/n_gpus)*keep][draw_len], and 1 / 2 are not available):
  *   which = 0: kept draws   [chains*keep][draw_len]   (draw_len floats per draw, Stan block order:

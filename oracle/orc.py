@@ -52,7 +52,7 @@ def lib():
                                  f64p, i64p, f64p]
         L.orc_sample.restype = C.c_double
         L.orc_transitions.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_double, f64p, f64p, C.c_uint32,
-                                      C.c_int, f64p, f64p]
+                                      C.c_int, f64p, f64p, C.c_int]
         L.orc_rng_words.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     C.POINTER(C.c_uint32)]
         _lib = L
@@ -113,13 +113,13 @@ class OracleModel:
                                 nlf.ctypes.data_as(C.POINTER(C.c_int64)), _p(im) if save_inv_metric else None)
         return dict(inv_metric=im, theta=theta, monitor=mon, stats=stats, stepsize=eps, n_leapfrog=nlf, seconds=secs, threads=threads)
 
-    def transitions(self, q0, eps, inv_metric, n_iter=1, seed=1843, chain=0, tree_mode=1, max_depth=10, iter0=0):
+    def transitions(self, q0, eps, inv_metric, n_iter=1, seed=1843, chain=0, tree_mode=1, max_depth=10, iter0=0, literal=False):
         q0 = np.ascontiguousarray(q0, dtype=np.float64)
         im = np.ascontiguousarray(inv_metric, dtype=np.float64)
         q_out = np.empty((n_iter, self.D))
         stats = np.empty((n_iter, 7))
         lib().orc_transitions(self.h, int(seed), int(chain), int(tree_mode), int(max_depth), float(eps), _p(im), _p(q0),
-                              int(iter0), int(n_iter), _p(q_out), _p(stats))
+                              int(iter0), int(n_iter), _p(q_out), _p(stats), int(literal))
         return q_out, stats
 
 

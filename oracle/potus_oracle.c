@@ -703,10 +703,11 @@ ORC_API double orc_sample(const OrcModel* m, const PotusConfig* cfg, int literal
  * chain from a given point with fixed step size and inverse metric; returns stats[n_iter][7] and
  * the points after each transition. */
 ORC_API void orc_transitions(const OrcModel* m, uint64_t seed, uint32_t chain, int tree_mode, int max_depth, double eps,
-                             const double* inv_metric, const double* q0, uint32_t iter0, int n_iter, double* q_out, double* stats) {
+                             const double* inv_metric, const double* q0, uint32_t iter0, int n_iter, double* q_out, double* stats,
+                             int literal) {
   Chain c; memset(&c, 0, sizeof(c));
   const int D = m->D;
-  c.m = m; c.wk = work_new(m); c.D = D; c.seed = seed; c.chain = chain; c.literal = 0; c.tree_mode = tree_mode; c.max_depth = max_depth;
+  c.m = m; c.wk = work_new(m); c.D = D; c.seed = seed; c.chain = chain; c.literal = literal; c.tree_mode = tree_mode; c.max_depth = max_depth;
   c.inv_metric = vnew(D); memcpy(c.inv_metric, inv_metric, sizeof(double) * D);
   c.q = vnew(D); c.p = vnew(D); c.g = vnew(D); c.eps = eps;
   c.arena_cap = (size_t)(max_depth + 2) * 6 * D; c.arena = (double*)malloc(sizeof(double) * c.arena_cap); c.arena_top = 0;

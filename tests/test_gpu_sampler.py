@@ -344,3 +344,72 @@ def test_in_library_multi_gpu_is_the_same_chains(pkg, datalists, cuda_lib):
         assert np.array_equal(a[k], b[k]), k
     assert np.array_equal(one.inv_metric(), two.inv_metric())
     assert one.stats["n_leapfrog_total"] == two.stats["n_leapfrog_total"]
+
+
+@pytest.mark.parametrize("force_stream", [False, True])
+def test_sampling_phase_transitions_follow_the_oracle(pkg, orc_mod, datalists, cuda_lib, force_stream):
+    """The STATIONARY phase, decision by decision: chains seeded (potus_set_state) with the committed adapted oracle states
+    (tests/golden/oracle_adapted_states_2016.npz: position after 500 warm-up iterations, step size ~0.014, adapted metric) run
+    sampling transitions on the device and in the fp64 oracle with the same Philox streams.  These are the depth-8 trajectories
+    that end through an in-subtree U-turn -- the exit path almost every production transition takes.  First transition: tree
+    depth, n_leapfrog, divergence identical and accept_stat within 0.01 for every chain; over 3 transitions at most one chain
+    may have left the oracle's path (fp32 round-off amplified over ~750 leapfrogs)."""
+    d = datalists[2016]
+    st = np.load(os.path.join(GOLDEN, "oracle_adapted_states_2016.npz"))
+    C, n_it = 8, 3
+    state = dict(theta=st["q"][:C].astype(np.float64), stepsize=st["stepsize"][:C], inv_metric=st["inv_metric"][:C].astype(np.float64))
+    fit = pkg.cmdstan_model().sample(data=d, seed=99, chains=C, iter_warmup=0, iter_sampling=n_it, keep_per_chain=n_it, state=state,
+                                     force_stream=force_stream)
+    sp = fit.sampler_params()
+    om = orc_mod.OracleModel(d)
+    off_path = 0
+    for c in range(C):
+        q_o, s_o = om.transitions(state["theta"][c], state["stepsize"][c], state["inv_metric"][c], n_iter=n_it, seed=99, chain=c, tree_mode=1, iter0=0)
+        assert sp["treedepth__"][c, 0] == s_o[0, 3] and sp["n_leapfrog__"][c, 0] == s_o[0, 4] and sp["divergent__"][c, 0] == s_o[0, 5] == 0
+        assert abs(sp["accept_stat__"][c, 0] - s_o[0, 1]) < 0.01 and abs(sp["lp__"][c, 0] - s_o[0, 0]) < 0.05
+        assert np.all(sp["stepsize__"][c] == np.float32(state["stepsize"][c]))
+        off_path += not np.array_equal(sp["n_leapfrog__"][c], s_o[:, 4])
+        assert np.all(sp["treedepth__"][c] >= 7)      # stationary trajectories: ~pi/eps leapfrogs
+    assert off_path <= 1, off_path
+    assert np.all(sp["n_leapfrog__"] < 2 ** sp["treedepth__"] + 0.5)   # in-subtree exits happen: not every tree is complete
+    th = fit.theta().reshape(C, n_it, -1)
+    assert np.abs(th[:, 0] - np.stack([om.transitions(state["theta"][c], state["stepsize"][c], state["inv_metric"][c], n_iter=1, seed=99, chain=c,
+                                                      tree_mode=1, iter0=0)[0][0] for c in range(C)])).max() < 5e-3
+
+
+def test_on_device_postprocessing_matches_the_host_restatement(pkg, datalists, cuda_lib):
+    """potus_postprocess (csrc/potus_post.cu: SURVEY 8(f) row f2 on the device, over every sampling iteration) against the host
+    numpy restatement of the reports' computations (postprocess.py: README.Rmd:206-300) and diagnostics.py (Stan ESS / split
+    R-hat) on the same monitor buffer: means/sd 1e-6, quantiles 2e-6 (exact order statistics of fp32 shares), P(win) and the
+    electoral-college numbers exact up to draws whose share is within 1e-6 of 0.5, ESS 1e-6 relative, R-hat 1e-9; and the
+    device-formed predicted_score equals inv_logit(mu_b)' of the kept draws."""
+    d = datalists[2016]
+    fit = pkg.cmdstan_model().sample(data=d, seed=3, chains=24, iter_warmup=150, iter_sampling=60, keep_per_chain=3)
+    ev = d["_ev_state"].astype(float)
+    sm = fit.summary(ev=ev, ev_threshold=270.0)
+    mon = fit.monitor()
+    sh = pkg.postprocess.election_day_shares(mon)
+    tab = pkg.postprocess.state_table(sh, d["_state_names"])
+    assert np.abs(sm["states"]["mean"] - tab["mean"]).max() < 1e-6 and np.abs(sm["states"]["sd"] - sh.std(0, ddof=1)).max() < 1e-6
+    assert np.abs(sm["states"]["q025"] - tab["low"]).max() < 2e-6 and np.abs(sm["states"]["q975"] - tab["high"]).max() < 2e-6
+    for q, nm in ((0.05, "q05"), (0.5, "q50"), (0.95, "q95")):
+        assert np.abs(sm["states"][nm] - np.quantile(sh, q, axis=0)).max() < 2e-6
+    edge = (np.abs(sh - 0.5) < 1e-6).mean(0)
+    assert np.all(np.abs(sm["states"]["prob"] - tab["prob"]) <= edge + 1e-12)
+    nat = pkg.postprocess.national_vote(sh, d["state_weights"])
+    assert abs(sm["national"]["mean"] - nat["mean"]) < 1e-6 and abs(sm["national"]["q025"] - nat["low"]) < 2e-6 and abs(sm["national"]["q975"] - nat["high"]) < 2e-6
+    assert abs(sm["national"]["prob"] - nat["prob"]) <= (np.abs(nat["draws"] - 0.5) < 1e-6).mean() + 1e-12
+    ec = pkg.postprocess.electoral_college(sh, ev)
+    n_edge = (np.abs(sh - 0.5) < 1e-6).any(1).mean()
+    assert abs(sm["electoral_votes"]["mean"] - ec["mean"]) <= 60 * n_edge + 1e-6 and abs(sm["electoral_votes"]["prob"] - ec["prob"]) <= n_edge + 1e-12
+    assert abs(sm["electoral_votes"]["q50"] - ec["median"]) <= (1 if n_edge > 0 else 1e-9)
+    e_host = np.array([pkg.diagnostics.ess(mon[:, :, k]) for k in range(52)])
+    r_host = np.array([pkg.diagnostics.rhat(mon[:, :, k]) for k in range(52)])
+    assert np.abs(sm["ess"] / e_host - 1).max() < 1e-6, np.abs(sm["ess"] / e_host - 1).max()
+    assert np.abs(sm["rhat"] - r_host).max() < 1e-9
+    assert np.abs(sm["monitor_mean"] - mon.reshape(-1, 52).mean(0)).max() < 1e-6
+    ps, mu = fit.extract("predicted_score"), fit.extract("mu_b")
+    assert ps.shape == (72, 254, 51) and np.abs(ps - 1 / (1 + np.exp(-np.transpose(mu, (0, 2, 1))))).max() < 1e-6
+    st, sp = fit.stats, fit.sampler_params()
+    assert st["n_leapfrog_total"] == int(sp["n_leapfrog__"].sum()) and st["n_leapfrog_sampling"] == int(sp["n_leapfrog__"][:, 150:].sum())
+    assert abs(st["mean_accept_stat"] - sp["accept_stat__"][:, 150:].mean()) < 1e-6 and abs(st["mean_treedepth"] - sp["treedepth__"][:, 150:].mean()) < 1e-9

@@ -1,5 +1,7 @@
 """Small run for compute-sanitizer that also reports how each transition ended (development aid).
-   python tools/sanitizer_run.py [chains] [iter_warmup] [iter_sampling]"""
+   python tools/sanitizer_run.py [chains] [iter_warmup] [iter_sampling] [adapted] [stream]
+`adapted`: seed the chains from the committed adapted oracle states (potus_set_state, iter_warmup forced to 0), so that the
+transitions are stationary depth-8 trajectories ending through the in-subtree U-turn break."""
 import os
 import sys
 
@@ -13,11 +15,19 @@ pkg = potus_pkg.load()
 chains = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 nw = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ns = int(sys.argv[3]) if len(sys.argv) > 3 else 1
+adapted = "adapted" in sys.argv[4:]
+stream = "stream" in sys.argv[4:]
 data = pkg.load_npz(os.path.join(ROOT, "tests", "golden", "datalist_2016.npz"))
-fit = pkg.cmdstan_model().sample(data=data, seed=1843, chains=chains, iter_warmup=nw, iter_sampling=ns, keep_per_chain=1)
+state = None
+if adapted:
+    st = np.load(os.path.join(ROOT, "tests", "golden", "oracle_adapted_states_2016.npz"))
+    idx = np.arange(chains) % st["q"].shape[0]
+    state = dict(theta=st["q"][idx].astype(np.float64), stepsize=st["stepsize"][idx], inv_metric=st["inv_metric"][idx].astype(np.float64))
+    nw = 0
+fit = pkg.cmdstan_model().sample(data=data, seed=1843, chains=chains, iter_warmup=nw, iter_sampling=ns, keep_per_chain=1, state=state, force_stream=stream)
 sp = fit.sampler_params()
 depth, nleap, div = sp["treedepth__"].astype(int), sp["n_leapfrog__"].astype(int), sp["divergent__"].astype(int)
 full = nleap == (2 ** depth - 1)          # every doubling completed: ended at the top level (persist / max depth)
-print(f"transitions {depth.size}: divergent {int(div.sum())}; ended inside a subtree (in-loop break, n_leapfrog < 2^depth - 1) "
-      f"{int((~full & (div == 0)).sum())}; ended at the top level {int((full & (div == 0)).sum())}; "
-      f"leapfrogs {int(nleap.sum())}; depth histogram {np.bincount(depth.ravel()).tolist()}", flush=True)
+print(f"{'stream' if stream else 'resident'} kernel, {'adapted states' if adapted else 'random inits'}: transitions {depth.size}: divergent {int(div.sum())}; "
+      f"ended inside a subtree (in-loop U-turn break, n_leapfrog < 2^depth - 1) {int((~full & (div == 0)).sum())}; ended at the top level "
+      f"{int((full & (div == 0)).sum())}; leapfrogs {int(nleap.sum())}; depth histogram {np.bincount(depth.ravel()).tolist()}", flush=True)

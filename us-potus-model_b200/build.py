@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libpotus_b200.so")
-SOURCES = ["potus_lib.cu", "potus_kernel.cu", "potus_stream.cu", "potus_host.cu", "potus_stream_host.cuh", "potus_layout.h",
+SOURCES = ["potus_lib.cu", "potus_kernel.cu", "potus_stream.cu", "potus_post.cu", "potus_host.cu", "potus_stream_host.cuh", "potus_layout.h",
            "potus_stream_layout.h", "ptx_sm100.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--shared", "-Xptxas", "-v"]

@@ -138,8 +138,8 @@ def make_config(chains=4, iter_warmup=500, iter_sampling=500, seed=1843, keep_pe
 
 _lib = None
 
-EXPORTS = ("potus_create", "potus_run", "potus_draws_size", "potus_get_draws", "potus_get_stats",
-           "potus_device_buffer", "potus_destroy", "potus_last_error", "potus_logp_grad", "potus_logp_grad_ex", "potus_num_params")
+EXPORTS = ("potus_create", "potus_run", "potus_set_state", "potus_draws_size", "potus_get_draws", "potus_get_stats",
+           "potus_device_buffer", "potus_postprocess", "potus_destroy", "potus_last_error", "potus_logp_grad", "potus_logp_grad_ex", "potus_num_params")
 
 
 def load_library(path: str | None = None):
@@ -157,6 +157,8 @@ def load_library(path: str | None = None):
     lib.potus_create.restype = C.c_int
     lib.potus_run.argtypes = [C.c_void_p]
     lib.potus_run.restype = C.c_int
+    lib.potus_set_state.argtypes = [C.c_void_p, _f64p, _f64p, _f64p]
+    lib.potus_set_state.restype = C.c_int
     lib.potus_draws_size.argtypes = [C.c_void_p, C.c_char_p]
     lib.potus_draws_size.restype = C.c_size_t
     lib.potus_get_draws.argtypes = [C.c_void_p, C.c_char_p, _f64p, C.c_size_t]
@@ -165,6 +167,8 @@ def load_library(path: str | None = None):
     lib.potus_get_stats.restype = C.c_int
     lib.potus_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     lib.potus_device_buffer.restype = C.c_int
+    lib.potus_postprocess.argtypes = [C.c_void_p, _f64p, C.c_double, _f64p, _f64p]
+    lib.potus_postprocess.restype = C.c_int
     lib.potus_destroy.argtypes = [C.c_void_p]
     lib.potus_destroy.restype = None
     lib.potus_last_error.argtypes = []

@@ -482,6 +482,8 @@ struct PotusSampler {
   std::vector<ncclComm_t> comms;
   std::vector<float*> gath;
   size_t pad_floats = 0;
+  std::vector<float> h_w;       // state_weights (national vote of the post-processing)
+  bool have_state = false;      // potus_set_state: chains start from given states; potus_run skips inits and warm-up
   int alloc_chains = 0;         // chains the draw buffer is sized for (>= chains; equal shard size for ncclAllGather)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   int launches = 0;
@@ -613,6 +615,7 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
   s->cfg = *config;
   s->n_sm = n_sm;
   s->stream = use_stream;
+  s->h_w.assign(data->state_weights, data->state_weights + data->S);
   if (use_stream) {
     rc = build_stream_model(data, s->sh);
     if (rc) { potus_destroy(s); return rc; }
@@ -699,7 +702,7 @@ static int run_launch(PotusSampler* s) {
   s->launches = 0;
   CUDA_TRY(cudaMemsetAsync(s->prof, 0, 64 * sizeof(unsigned long long)));
   CUDA_TRY(cudaEventRecord(s->ev[0]));
-  {
+  if (!s->have_state) {
     CUDA_TRY(cudaMemsetAsync(s->queue, 0, sizeof(int)));
     if (s->stream) potus_stream_kernel<<<s->grid, SNT, SSMEM_BYTES>>>(make_sargs(s, 0, nw, 1));
     else potus_nuts_kernel<<<s->grid, NT, SMEM_BYTES>>>(make_args(s, 0, nw, 1));
@@ -726,24 +729,30 @@ static int run_finish(PotusSampler* s) {
   CUDA_TRY(cudaGetLastError());
   float ms01 = 0, ms12 = 0;
   CUDA_TRY(cudaEventElapsedTime(&ms01, s->ev[0], s->ev[1])); CUDA_TRY(cudaEventElapsedTime(&ms12, s->ev[1], s->ev[2]));
-  // summary statistics from the per-iteration sampler diagnostics
+  // summary statistics from the per-iteration sampler diagnostics, reduced on the device (the table itself goes to the host
+  // only when potus_get_draws("sampler_params") asks for it)
   const int C = s->cfg.chains;
-  s->h_sparams.resize((size_t)C * nt * 8);
-  CUDA_TRY(cudaMemcpy(s->h_sparams.data(), s->sparams, s->h_sparams.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  s->h_sparams.clear();
+  double hst[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  {
+    double* dst = nullptr;
+    CUDA_TRY(cudaMalloc(&dst, 8 * sizeof(double)));
+    potus_post_runstats_kernel<<<1, PNT>>>(s->sparams, C, nt, nw, dst);
+    cudaError_t e = cudaMemcpy(hst, dst, 8 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dst);
+    if (e != cudaSuccess) return fail(POTUS_ERR_CUDA, std::string("potus_post_runstats_kernel: ") + cudaGetErrorString(e));
+    ++s->launches;
+  }
   std::vector<ChainState> hcs(C);
   CUDA_TRY(cudaMemcpy(hcs.data(), s->cs, (size_t)C * sizeof(ChainState), cudaMemcpyDeviceToHost));
   PotusStats& st = s->stats;
   st = PotusStats{};
-  double acc = 0, dep = 0, eps = 0;
+  double acc = hst[3], dep = hst[4], eps = 0;
   for (int c = 0; c < C; ++c) {
     if (hcs[c].status != 0) return fail(POTUS_ERR_INIT, "a chain found no finite initial point in 100 attempts (Stan: 'Initialization failed')");
-    for (int it = 0; it < nt; ++it) {
-      const float* p = &s->h_sparams[((size_t)c * nt + it) * 8];
-      st.n_leapfrog_total += (int64_t)p[4];
-      if (it >= nw) { st.n_leapfrog_sampling += (int64_t)p[4]; st.n_divergent_sampling += (int64_t)p[5]; acc += p[1]; dep += p[3]; }
-    }
     eps += hcs[c].eps;
   }
+  st.n_leapfrog_total = (int64_t)hst[0]; st.n_leapfrog_sampling = (int64_t)hst[1]; st.n_divergent_sampling = (int64_t)hst[2];
   const double ns = (double)C * std::max(1, nt - nw);
   st.mean_accept_stat = acc / ns; st.mean_treedepth = dep / ns; st.mean_stepsize = eps / C;
   st.gpu_launches = s->launches;
@@ -817,6 +826,154 @@ int potus_run(PotusSampler* s) {
   int rc = run_launch(s);
   if (rc) return rc;
   return run_finish(s);
+}
+
+// Start every chain from a given state instead of random inits + warm-up: theta [chains][D] (Stan unconstrained order),
+// stepsize [chains], inv_metric [chains][D].  Requires iter_warmup == 0 (adaptation is what produced the state).
+int potus_set_state(PotusSampler* s, const double* theta, const double* stepsize, const double* inv_metric) {
+  if (!s || !theta || !stepsize || !inv_metric) return fail(POTUS_ERR_STATE, "NULL argument");
+  if (!s->subs.empty()) return fail(POTUS_ERR_STATE, "potus_set_state: not available with n_gpus > 1");
+  if (s->cfg.iter_warmup != 0) return fail(POTUS_ERR_STATE, "potus_set_state requires iter_warmup == 0");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  const int C = s->cfg.chains, VL = s->VL, D = s->D;
+  std::vector<float> q((size_t)C * VL, 0.f), sm((size_t)C * VL, 0.f);
+  std::vector<ChainState> cs(C);
+  for (int c = 0; c < C; ++c) {
+    for (int k = 0; k < VL; ++k) {
+      const int si = (*s->map)[k];
+      if (si >= 0) {
+        const double im = inv_metric[(size_t)c * D + si];
+        if (!(im > 0) || !std::isfinite(theta[(size_t)c * D + si])) return fail(POTUS_ERR_INVALID_DATA, "potus_set_state: inv_metric must be positive and theta finite");
+        q[(size_t)c * VL + k] = (float)theta[(size_t)c * D + si];
+        sm[(size_t)c * VL + k] = (float)std::sqrt(im);
+      }
+    }
+    if (!(stepsize[c] > 0)) return fail(POTUS_ERR_INVALID_DATA, "potus_set_state: stepsize must be positive");
+    ChainState z{};
+    z.eps = (float)stepsize[c]; z.da_mu = std::log(10.0 * stepsize[c]); z.status = 0; z.w_next = -1;
+    cs[c] = z;
+  }
+  CUDA_TRY(cudaMemcpy(s->q, q.data(), q.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->sqrt_m, sm.data(), sm.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(s->cs, cs.data(), cs.size() * sizeof(ChainState), cudaMemcpyHostToDevice));
+  s->have_state = true;
+  return POTUS_OK;
+}
+
+// Stan's multi-chain effective sample size from the chain-averaged autocovariance (stan/analyze/mcmc/compute_effective_sample_size.hpp;
+// the same steps as us-potus-model_b200/diagnostics.py: Geyer's initial positive + monotone sequence)
+static double ess_from_acov(const std::vector<double>& acov_mean, double mean_var, double var_between, int c, int n) {
+  double var_plus = mean_var * (n - 1.0) / n;
+  if (c > 1) var_plus += var_between;
+  if (!(var_plus > 0) || n < 4) return std::nan("");
+  std::vector<double> rho(n + 2, 0.0);
+  int t = 1;
+  double rho_even = 1.0, rho_odd = 1 - (mean_var - acov_mean[1]) / var_plus;
+  rho[0] = rho_even; rho[1] = rho_odd;
+  while (t < n - 4 && (rho_even + rho_odd) > 0) {
+    rho_even = 1 - (mean_var - acov_mean[t + 1]) / var_plus;
+    rho_odd = 1 - (mean_var - acov_mean[t + 2]) / var_plus;
+    if (rho_even + rho_odd >= 0) { rho[t + 1] = rho_even; rho[t + 2] = rho_odd; }
+    t += 2;
+  }
+  const int max_t = t;
+  if (rho_even > 0) rho[max_t + 1] = rho_even;
+  t = 1;
+  while (t <= max_t - 3) {
+    if (rho[t + 1] + rho[t + 2] > rho[t - 1] + rho[t]) { rho[t + 1] = (rho[t - 1] + rho[t]) / 2; rho[t + 2] = rho[t + 1]; }
+    t += 2;
+  }
+  double tau = -1;
+  for (int i = 0; i < max_t; ++i) tau += 2 * rho[i];
+  tau += rho[max_t + 1];
+  tau = std::max(tau, 1.0 / std::log10((double)c * n));
+  return (double)c * n / tau;
+}
+
+// On-device post-processing over ALL chains x iter_sampling monitored draws (csrc/potus_post.cu).
+//   ev            [S] electoral votes (README.Rmd:271-300) or NULL; ev_threshold e.g. 270
+//   state_table   [(S+2)][8] row-major: mean, sd, 2.5%, 5%, 50%, 95%, 97.5%, P(> 0.5)  of inv_logit(mu_b[s,T]) for the S states,
+//                 row S = national vote (state_weights-weighted mean of the shares per draw), row S+1 = democratic electoral votes
+//                 (its last column: P(ev >= ev_threshold); zeros without ev)
+//   ess_table     [(S+1)][3] row-major: Stan ESS, split R-hat, posterior mean of the monitored scalars (logit scale; row S =
+//                 national_mu_b_average[T]); may be NULL
+int potus_postprocess(PotusSampler* s, const double* ev, double ev_threshold, double* state_table, double* ess_table) {
+  if (!s || !state_table) return fail(POTUS_ERR_STATE, "NULL argument");
+  if (!s->ran) return fail(POTUS_ERR_STATE, "potus_run has not completed");
+  if (!s->subs.empty()) return fail(POTUS_ERR_STATE, "potus_postprocess: not available with n_gpus > 1 (run it per device)");
+  const int C = s->cfg.chains, n = s->cfg.iter_sampling, S = s->S, Q = S + 2;
+  const long long R = (long long)C * n;
+  if (R < 2) return fail(POTUS_ERR_STATE, "potus_postprocess needs at least two monitored draws");
+  CUDA_TRY(cudaSetDevice(s->cfg.device));
+  std::vector<float> hw(s->h_w), hev(S, 0.f), thr(Q, 0.5f);
+  if (ev) for (int i = 0; i < S; ++i) hev[i] = (float)ev[i];
+  thr[S + 1] = (float)(ev_threshold - 0.5);
+  static const double qs[5] = {0.025, 0.05, 0.5, 0.95, 0.975};
+  std::vector<long long> ranks(5);
+  std::vector<double> frac(5);
+  for (int j = 0; j < 5; ++j) { const double h = (R - 1) * qs[j]; const long long lo = (long long)std::floor(h); ranks[j] = lo + 1; frac[j] = h - lo; }
+  const int cpg = 8, G = (C + cpg - 1) / cpg;
+  float *dsh = nullptr, *dw = nullptr, *dev = nullptr, *dthr = nullptr;
+  double *dmom = nullptr, *dsel = nullptr, *dcs = nullptr, *dac = nullptr;
+  long long* drank = nullptr;
+  auto cleanup = [&]() { cudaFree(dsh); cudaFree(dw); cudaFree(dev); cudaFree(dthr); cudaFree(dmom); cudaFree(dsel); cudaFree(dcs); cudaFree(dac); cudaFree(drank); };
+  cudaError_t e;
+#define PP_TRY(x) do { e = (x); if (e != cudaSuccess) { cleanup(); return fail(POTUS_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e)); } } while (0)
+  PP_TRY(cudaMalloc(&dsh, (size_t)Q * R * sizeof(float)));
+  PP_TRY(cudaMalloc(&dw, S * sizeof(float))); PP_TRY(cudaMalloc(&dev, S * sizeof(float))); PP_TRY(cudaMalloc(&dthr, Q * sizeof(float)));
+  PP_TRY(cudaMalloc(&dmom, (size_t)Q * 3 * sizeof(double))); PP_TRY(cudaMalloc(&dsel, (size_t)Q * 5 * 2 * sizeof(double)));
+  PP_TRY(cudaMalloc(&drank, 5 * sizeof(long long)));
+  PP_TRY(cudaMemcpy(dw, hw.data(), S * sizeof(float), cudaMemcpyHostToDevice));
+  PP_TRY(cudaMemcpy(dev, hev.data(), S * sizeof(float), cudaMemcpyHostToDevice));
+  PP_TRY(cudaMemcpy(dthr, thr.data(), Q * sizeof(float), cudaMemcpyHostToDevice));
+  PP_TRY(cudaMemcpy(drank, ranks.data(), 5 * sizeof(long long), cudaMemcpyHostToDevice));
+  potus_post_shares_kernel<<<1184, 256>>>(s->monitor, dw, ev ? dev : nullptr, S, R, dsh);
+  potus_post_moments_kernel<<<Q, PNT>>>(dsh, R, dthr, dmom);
+  potus_post_select_kernel<<<Q * 5, PNT>>>(dsh, R, drank, 5, dsel);
+  std::vector<double> mom((size_t)Q * 3), sel((size_t)Q * 10);
+  PP_TRY(cudaMemcpy(mom.data(), dmom, mom.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  PP_TRY(cudaMemcpy(sel.data(), dsel, sel.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  for (int q = 0; q < Q; ++q) {
+    double* row = state_table + (size_t)q * 8;
+    row[0] = mom[q * 3]; row[1] = mom[q * 3 + 1]; row[7] = mom[q * 3 + 2];
+    for (int j = 0; j < 5; ++j) { const double a = sel[(q * 5 + j) * 2], b = sel[(q * 5 + j) * 2 + 1]; row[2 + j] = a + frac[j] * (b - a); }
+    if (q == S + 1 && !ev) for (int j = 0; j < 8; ++j) row[j] = 0;
+  }
+  if (ess_table) {
+    if (n < 4 || n > 2048) { cleanup(); return fail(POTUS_ERR_UNSUPPORTED, "ESS on the device needs 4 <= iter_sampling <= 2048"); }
+    const int S1 = S + 1;
+    PP_TRY(cudaMalloc(&dcs, (size_t)S1 * C * 6 * sizeof(double)));
+    PP_TRY(cudaMalloc(&dac, (size_t)S1 * G * n * sizeof(double)));
+    potus_post_acov_kernel<<<dim3(S1, G), 512, n * sizeof(float)>>>(s->monitor, C, n, S1, cpg, dcs, dac);
+    std::vector<double> cs((size_t)S1 * C * 6), ac((size_t)S1 * G * n);
+    PP_TRY(cudaMemcpy(cs.data(), dcs, cs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    PP_TRY(cudaMemcpy(ac.data(), dac, ac.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<double> am(n);
+    for (int q = 0; q < S1; ++q) {
+      for (int l = 0; l < n; ++l) { double a = 0; for (int g = 0; g < G; ++g) a += ac[((size_t)q * G + g) * n + l]; am[l] = a / C; }
+      double mean_var = 0, mm = 0;
+      for (int c = 0; c < C; ++c) { const double* o = &cs[((size_t)q * C + c) * 6]; mean_var += o[1] * n / (n - 1.0); mm += o[0]; }
+      mean_var /= C; mm /= C;
+      double vb = 0;
+      for (int c = 0; c < C; ++c) { const double d = cs[((size_t)q * C + c) * 6] - mm; vb += d * d; }
+      vb = C > 1 ? vb / (C - 1) : 0;
+      // split R-hat over the 2C half chains (first h and last h iterations)
+      const int h = n / 2;
+      double w = 0, hm = 0;
+      for (int c = 0; c < C; ++c) { const double* o = &cs[((size_t)q * C + c) * 6]; w += (o[3] + o[5]) * h / (h - 1.0); hm += o[2] + o[4]; }
+      w /= 2 * C; hm /= 2 * C;
+      double b = 0;
+      for (int c = 0; c < C; ++c) { const double* o = &cs[((size_t)q * C + c) * 6]; b += (o[2] - hm) * (o[2] - hm) + (o[4] - hm) * (o[4] - hm); }
+      b = h * b / (2 * C - 1);
+      double* row = ess_table + (size_t)q * 3;
+      row[0] = ess_from_acov(am, mean_var, vb, C, n);
+      row[1] = std::sqrt(((h - 1.0) / h * w + b / h) / w);
+      row[2] = mm;
+    }
+  }
+  cleanup();
+#undef PP_TRY
+  return POTUS_OK;
 }
 
 int potus_get_stats(PotusSampler* s, PotusStats* out) {
@@ -915,6 +1072,10 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   }
   if (p == "sampler_params") {  // [(iter)*chains, 7], row index = chain*nt + it (draw-fastest within a column)
     const size_t R = (size_t)C * nt;
+    if (s->h_sparams.size() != R * 8) {
+      s->h_sparams.resize(R * 8);
+      CUDA_TRY(cudaMemcpy(s->h_sparams.data(), s->sparams, s->h_sparams.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    }
     const double c0 = s->lp_const;  // device values are centred: lp__ = -U + c0, energy__ = H - c0
     for (size_t r = 0; r < R; ++r)
       for (int k = 0; k < 7; ++k) {
@@ -944,13 +1105,21 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
       for (int k = 0; k <= S; ++k) out[r + R * k] = s->h_monitor[r * (S + 1) + k];
     return POTUS_OK;
   }
-  if (!s->have_host) {
-    s->h_draws.resize((size_t)C * s->keep * s->draw_len);
-    CUDA_TRY(cudaMemcpy(s->h_draws.data(), s->draws, s->h_draws.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    s->have_host = true;
+  if (p == "predicted_score" && s->subs.empty()) {  // [draws, T, S] = inv_logit(mu_b[s,t]); poll_model_2020.stan:136-139
+    // formed on the device from the kept-draw records, already in extract()'s layout; fp32 over the bus, widened here
+    const size_t R = (size_t)C * s->keep, ne = R * S * T;
+    float* dps = nullptr;
+    CUDA_TRY(cudaMalloc(&dps, std::max<size_t>(ne * sizeof(float), 16)));
+    potus_post_pscore_kernel<<<1184, 256>>>(s->draws, (long long)R, s->draw_len, S, T, dps);
+    std::vector<float> hps(ne);
+    cudaError_t e = cudaMemcpy(hps.data(), dps, ne * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dps);
+    if (e != cudaSuccess) return fail(POTUS_ERR_CUDA, std::string("potus_post_pscore_kernel: ") + cudaGetErrorString(e));
+    for (size_t i = 0; i < ne; ++i) out[i] = hps[i];
+    return POTUS_OK;
   }
   const size_t R = (size_t)C * s->keep;
-  if (p == "predicted_score") {  // [draws, T, S] = inv_logit(mu_b[s,t]); poll_model_2020.stan:136-139
+  if (p == "predicted_score") {  // (n_gpus > 1: from the gathered records on the host)
     for (size_t r = 0; r < R; ++r) {
       const float* dr = &s->h_draws[r * s->draw_len];
       for (int t = 0; t < T; ++t)
@@ -963,9 +1132,18 @@ int potus_get_draws(PotusSampler* s, const char* par, double* out, size_t n) {
   }
   ParInfo pi;
   par_info(s, par, pi);
+  if (s->subs.empty()) {   // only the requested block of every draw record crosses the bus (strided device-to-host copy)
+    std::vector<float> tmp(R * pi.len);
+    if (!tmp.empty())
+      CUDA_TRY(cudaMemcpy2D(tmp.data(), pi.len * sizeof(float), s->draws + pi.off, (size_t)s->draw_len * sizeof(float), pi.len * sizeof(float), R,
+                            cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < R; ++r)
+      for (size_t k = 0; k < pi.len; ++k) out[r + R * k] = tmp[r * pi.len + k];  // mu_b: k = s + S*t == R's [draw, s, t] order
+    return POTUS_OK;
+  }
   for (size_t r = 0; r < R; ++r) {
     const float* dr = &s->h_draws[r * s->draw_len + pi.off];
-    for (size_t k = 0; k < pi.len; ++k) out[r + R * k] = dr[k];  // mu_b: k = s + S*t == R's [draw, s, t] order
+    for (size_t k = 0; k < pi.len; ++k) out[r + R * k] = dr[k];
   }
   return POTUS_OK;
 }

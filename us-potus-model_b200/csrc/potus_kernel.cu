@@ -190,6 +190,49 @@ __device__ __forceinline__ void affine_scan(float& A, float& B, int l) {
   }
 }
 
+// One poll: centred log-likelihood term f = ll(eta) - ll(eta_hat) and residual r = d f / d eta, with d = eta - eta_hat,
+// p = p_hat = inv_logit(eta_hat), y/n = p + rho_hat:   f = n [ rho_hat d - g(d) ],  r = n [ rho_hat - g'(d) ],
+// g(d) = log(1 - p + p e^d) - p d  =  sum_{k>=2} kappa_k d^k / k!   (the cumulant series of Bernoulli(p); kappa_2 = v = p(1-p),
+// kappa_3 = v w, kappa_4 = v (1 - 6v), kappa_5 = v w (1 - 12 v), ... with w = 1 - 2p).
+//   |d| < 0.4 (every poll of a chain near its typical set): the series through d^10 and ITS OWN derivative -- an exactly consistent
+//     energy / gradient pair, truncation error < 7e-10 v, ~45 FMAs, no divergence inside a warp;
+//   0.4 <= |d| < 12: the closed form with expm1f / log1pf (warm-up transients);
+//   beyond: direct softplus difference (accuracy irrelevant out there).
+__device__ __forceinline__ void poll_term(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
+  const float d = eta - eh;
+  const float ad = fabsf(d);
+  if (ad < 0.4f) {
+    const float v = ph * (1.0f - ph), w = 1.0f - 2.0f * ph, x2 = d * d;
+    const float e4 = fmaf(-6.0f, v, 1.0f) * (1.0f / 24.0f);
+    const float e6 = fmaf(v, fmaf(120.0f, v, -30.0f), 1.0f) * (1.0f / 720.0f);
+    const float e8 = fmaf(v, fmaf(v, fmaf(-5040.0f, v, 1680.0f), -126.0f), 1.0f) * (1.0f / 40320.0f);
+    const float e10 = fmaf(v, fmaf(v, fmaf(v, fmaf(362880.0f, v, -151200.0f), 17640.0f), -510.0f), 1.0f) * (1.0f / 3628800.0f);
+    const float o5 = fmaf(-12.0f, v, 1.0f) * (1.0f / 120.0f);
+    const float o7 = fmaf(v, fmaf(360.0f, v, -60.0f), 1.0f) * (1.0f / 5040.0f);
+    const float o9 = fmaf(v, fmaf(v, fmaf(-20160.0f, v, 5040.0f), -252.0f), 1.0f) * (1.0f / 362880.0f);
+    const float ev = x2 * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, e10, e8), e6), e4), 0.5f);
+    const float od = x2 * fmaf(x2, fmaf(x2, fmaf(x2, o9, o7), o5), 1.0f / 6.0f);
+    const float g = v * fmaf(w * d, od, ev);
+    const float dev = d * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 10.0f * e10, 8.0f * e8), 6.0f * e6), 4.0f * e4), 1.0f);
+    const float dod = x2 * fmaf(x2, fmaf(x2, fmaf(x2, 9.0f * o9, 7.0f * o7), 5.0f * o5), 0.5f);
+    const float gp = v * fmaf(w, dod, dev);
+    f = n * fmaf(rh, d, -g);
+    r = n * (rh - gp);
+  } else if (ad < 12.0f) {
+    // ll(eta) - ll(eta_hat) = n [ (y/n) d - log1p(p_hat expm1(d)) ]
+    const float em1 = expm1f(d);
+    const float uu = ph * em1;
+    f = n * (rh * d + (ph * d - log1pf(uu)));
+    r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
+  } else {  // far tail: direct, stable softplus difference
+    const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
+    const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
+    const float sg = 1.0f / (1.0f + __expf(-eta));
+    f = n * ((ph + rh) * d - (sp - sph));
+    r = n * ((ph + rh) - sg);
+  }
+}
+
 // Accumulator read-out shared by both GEMMs: (D1 + D2/2048) * scale (+ prior for day rows) -> fp32
 // scratch [row][53].  The scratch aliases the operand planes, so nothing is written before the LAST
 // commit (bar_mma[1]) has completed; tile-0 warps still overlap their TMEM loads with tile 1's MMAs.
@@ -454,7 +497,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
     const float* pbrow = scr + PB_ROW * SCR_PITCH;
     const bool full = m.full;
     // one poll: linear predictor, centred log-likelihood term f and residual r
-    auto poll_term = [&](int k, uint32_t ix, float& f, float& r, float& sigx) {
+    auto poll_eval = [&](int k, uint32_t ix, float& f, float& r, float& sigx) {
       const int s = ix & 63, d = (ix >> 6) & 255, p = (ix >> 14) & 1023, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
       sigx = (s == NAT_COL) ? m.sig_n : m.sig_s;
       float eta = scr[d * SCR_PITCH + s] + pbrow[s] + m.sig_c * qn[m.nz_c + p] + sigx * qn[m.nz_x + k];
@@ -462,21 +505,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
         eta += m.sig_m * qn[m.nz_m + mo] + m.sig_pop * qn[m.nz_pop + po];
         if ((ix >> 30) & 1) eta += sE()[d];
       }
-      const float n = sPKF(1)[k], eh = sPKF(2)[k], ph = sPKF(3)[k], rh = sPKF(4)[k];
-      const float dl = eta - eh;
-      if (fabsf(dl) < 12.0f) {
-        // ll(eta) - ll(eta_hat) = n [ (y/n) dl - log1p(p_hat expm1(dl)) ],  y/n = p_hat + rho_hat
-        const float em1 = expm1f(dl);
-        const float uu = ph * em1;
-        f = n * (rh * dl + (ph * dl - log1pf(uu)));
-        r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
-      } else {  // far tail: direct, stable softplus difference (accuracy irrelevant out here)
-        const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
-        const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
-        const float sg = 1.0f / (1.0f + __expf(-eta));
-        f = n * ((ph + rh) * dl - (sp - sph));
-        r = n * ((ph + rh) - sg);
-      }
+      poll_term(eta, sPKF(1)[k], sPKF(2)[k], sPKF(3)[k], sPKF(4)[k], f, r);
     };
     auto poll_accum = [&](int k, uint32_t ix, float f, float r, float sigx) {
       const int s = ix & 63, mo = (ix >> 24) & 7, po = (ix >> 27) & 7;
@@ -493,7 +522,7 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
     for (int k = tid; k < m.N; k += NT) {
       const uint32_t ix = sPKI()[k];
       float f, r, sx;
-      poll_term(k, ix, f, r, sx);
+      poll_eval(k, ix, f, r, sx);
       poll_accum(k, ix, f, r, sx);
     }
     PROF(16);

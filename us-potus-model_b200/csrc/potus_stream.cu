@@ -193,23 +193,6 @@ __device__ __forceinline__ float s_epilogue(float scale, const float* add_col, f
   return acc;
 }
 
-// one poll: centred log-likelihood term f and residual r (same arithmetic as potus_kernel.cu P5)
-__device__ __forceinline__ void s_poll_term(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
-  const float dl = eta - eh;
-  if (fabsf(dl) < 12.0f) {
-    const float em1 = expm1f(dl);
-    const float uu = ph * em1;
-    f = n * (rh * dl + (ph * dl - log1pf(uu)));
-    r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
-  } else {
-    const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
-    const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
-    const float sg = 1.0f / (1.0f + __expf(-eta));
-    f = n * ((ph + rh) * dl - (sp - sph));
-    r = n * ((ph + rh) - sg);
-  }
-}
-
 // element-wise tail of a leaf for one parameter: g = dU/dtheta at q, p/s read from global by the caller
 struct LeafAcc { float kk, c1a, c1b; };
 __device__ __forceinline__ void s_leaf_elem(float q, float g, float p, float s, float lr, bool odd, float hs, float eps_s, float& qn, float& pn,
@@ -329,6 +312,20 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
   for (int tile = 0; tile < m.NTILE; ++tile) {
     const int t0 = tile * ST_ROWS;
     const int p0 = __ldg(m.tile_ptr + tile), p1 = __ldg(m.tile_ptr + tile + 1);
+    // pull what the poll phase and the update phase of THIS tile will read into L2 now (the state vectors of 148 chains are
+    // far larger than L2, so every sweep streams them from HBM), and the innovations of the NEXT tile for its phase A
+    if (tid == 64) {
+      const int nrow = min(ST_ROWS, T - t0);
+      const uint32_t wb = (uint32_t)nrow * SP * 4, xb = (uint32_t)(((p1 - p0) * 4 + 15) & ~15);
+      const size_t w0 = (size_t)t0 * SP, x0 = ((size_t)m.o_x + p0) & ~(size_t)3;
+      if (LEAF) {
+        ptx::prefetch_l2_bulk(io.ph + w0, wb); ptx::prefetch_l2_bulk(io.sm + w0, wb);
+        if (odd) ptx::prefetch_l2_bulk(io.Lr + w0, wb);
+        if (xb) { ptx::prefetch_l2_bulk(io.ph + x0, xb); ptx::prefetch_l2_bulk(io.sm + x0, xb); if (odd) ptx::prefetch_l2_bulk(io.Lr + x0, xb); }
+      }
+      if (xb) ptx::prefetch_l2_bulk(qin + x0, xb);
+      if (tile + 1 < m.NTILE) ptx::prefetch_l2_bulk(qin + (size_t)(t0 + ST_ROWS) * SP, (uint32_t)min(ST_ROWS, T - t0 - ST_ROWS) * SP * 4);
+    }
     // ---------------- A: W tile -> fp16 hi/lo planes.  W[t] = a_T zT + a_w (colsum - sum_{u<t} Z[u])
     {
       // pass 1: day-quarter totals of the innovations (rows >= T-1 carry none)
@@ -415,18 +412,18 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       const float* mu = sF(SS_A);
       const float nat_pb = ctl.nat_pb;
       float* rpol = rbuf + m.rp_off;
-      constexpr int UD = 4;   // polls per thread in flight: every global load of a batch is issued before the first use
+      constexpr int UD = 2;   // polls per thread in flight (more costs registers, and spills go to L2: there is almost no L1 left)
       for (int kb = p0 + tid; kb < p1; kb += UD * SNT) {
         uint32_t w0[UD], pm[UD];
-        int pp[UD];
-        float x[UD], nn[UD], eh[UD], phh[UD], rh[UD], pv[UD], sv[UD], lrv[UD];
+        float4 pc[UD];
+        float x[UD], pv[UD], sv[UD], lrv[UD];
 #pragma unroll
         for (int u = 0; u < UD; ++u) {
           const int k = kb + u * SNT;
           if (k < p1) {
-            w0[u] = __ldg(m.pw0 + k); pp[u] = __ldg(m.ppol + k); pm[u] = __ldg(m.perm + k);
+            w0[u] = __ldg(m.pw0 + k); pm[u] = __ldg(m.perm + k);
+            pc[u] = __ldg(m.pc + k);
             x[u] = qin[m.o_x + k];
-            nn[u] = __ldg(m.pn + k); eh[u] = __ldg(m.peh + k); phh[u] = __ldg(m.pph + k); rh[u] = __ldg(m.prh + k);
             if (LEAF) { const size_t e = (size_t)m.o_x + k; pv[u] = io.ph[e]; sv[u] = io.sm[e]; lrv[u] = odd ? io.Lr[e] : 0.f; }
           }
         }
@@ -434,16 +431,16 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
         for (int u = 0; u < UD; ++u) {
           const int k = kb + u * SNT;
           if (k < p1) {
-            const int s = w0[u] & 511, dl = (w0[u] >> 9) & 127, mo = (w0[u] >> 16) & 7, po = (w0[u] >> 19) & 7;
+            const int s = w0[u] & 511, dl = (w0[u] >> 9) & 127, mo = (w0[u] >> 16) & 3, po = (w0[u] >> 18) & 3, pp = (w0[u] >> 21) & 511;
             const bool nat = (s == S);
             const float sigx = nat ? m.sig_n : m.sig_s;
-            float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp[u]] + sigx * x[u];
+            float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp] + sigx * x[u];
             if (m.full) {
               eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
-              if ((w0[u] >> 22) & 1) eta += sF(SS_E)[t0 + dl];
+              if ((w0[u] >> 20) & 1) eta += sF(SS_E)[t0 + dl];
             }
             float f, r;
-            s_poll_term(eta, nn[u], eh[u], phh[u], rh[u], f, r);
+            poll_term(eta, pc[u].x, pc[u].y, pc[u].z, pc[u].w, f, r);
             fsum += f;
             rbuf[k] = r;
             rpol[pm[u]] = r;
@@ -480,30 +477,23 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     {
       constexpr int UC = 4;
       for (int kb = p0 + tid; kb < p1; kb += UC * SNT) {
-        uint32_t key[UC], prev[UC], next[UC];
+        uint32_t wv[UC];
         float rr[UC];
 #pragma unroll
         for (int u = 0; u < UC; ++u) {
           const int k = kb + u * SNT;
-          key[u] = 0xffffffffu; prev[u] = 0xffffffffu; next[u] = 0xfffffffeu; rr[u] = 0.f;
-          if (k < p1) {
-            key[u] = __ldg(m.pw0 + k) & 0xffffu;
-            if (k > p0) prev[u] = __ldg(m.pw0 + k - 1) & 0xffffu;
-            if (k + 1 < p1) next[u] = __ldg(m.pw0 + k + 1) & 0xffffu;
-            rr[u] = rbuf[k];
-          }
+          wv[u] = 0u; rr[u] = 0.f;
+          if (k < p1) { wv[u] = __ldg(m.pw0 + k); rr[u] = rbuf[k]; }
         }
 #pragma unroll
         for (int u = 0; u < UC; ++u) {
           const int k = kb + u * SNT;
-          const int s = key[u] & 511;
-          if (k < p1 && key[u] != prev[u] && s < S) {   // head of a (state, day) run
+          if ((wv[u] >> 30) & 1) {   // head of a (state, day) run of state polls (bit 31: the run is this poll alone)
             float acc = rr[u];
-            if (next[u] == key[u]) {   // (runs longer than one poll are the exception)
-              acc += rbuf[k + 1];
-              for (int j = k + 2; j < p1 && (__ldg(m.pw0 + j) & 0xffffu) == key[u]; ++j) acc += rbuf[j];
-            }
-            const int dl = key[u] >> 9;
+            const uint32_t key = wv[u] & 0xffffu;
+            if (!(wv[u] >> 31))
+              for (int j = k + 1; j < p1 && (__ldg(m.pw0 + j) & 0xffffu) == key; ++j) acc += rbuf[j];
+            const int s = key & 511, dl = key >> 9;
             __half hi, lo;
             ptx::split_f16(acc * m.scale_G, hi, lo);
             const uint32_t o = (uint32_t)(s >> 3) * SA_LBO + (uint32_t)(dl >> 3) * SA_SBO + (uint32_t)(dl & 7) * 16 + (uint32_t)(s & 7) * 2;
@@ -524,7 +514,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) { const int k = kb + 32 * u; w8[u] = 0u; r8[u] = 0.f; if (k < k1) { w8[u] = __ldg(m.pw0 + k); r8[u] = rbuf[k]; } }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { if ((w8[u] >> 22) & 1) ae += r8[u]; if ((int)(w8[u] & 511) == S) an += r8[u]; }
+            for (int u = 0; u < 8; ++u) { if ((w8[u] >> 20) & 1) ae += r8[u]; if ((int)(w8[u] & 511) == S) an += r8[u]; }
           }
         }
 #pragma unroll
@@ -564,30 +554,46 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       float cz0 = 0.f, cz1 = 0.f;
       if (colload) {
         const size_t e0 = (size_t)(t0 + 32 * qd) * SP + c0;
-#pragma unroll 4
-        for (int d = 0; d < 32; ++d) {
-          const int t = t0 + 32 * qd + d;
-          if (t < T) {
-            const size_t e = e0 + (size_t)d * SP;
-            const float2 h = *reinterpret_cast<const float2*>(hp + d * pitch);
-            pre.x += h.x; pre.y += h.y;
-            const float2 z = *reinterpret_cast<const float2*>(qin + e);
-            qsq = fmaf(z.x, z.x, fmaf(z.y, z.y, qsq));
-            const bool walk = t < T - 1;
-            const float g0 = walk ? fmaf(-m.a_w, pre.x, z.x) : z.x, g1 = walk ? fmaf(-m.a_w, pre.y, z.y) : z.y;
-            if (LEAF) {
-              const float2 p = *reinterpret_cast<const float2*>(io.ph + e), sv = *reinterpret_cast<const float2*>(io.sm + e);
-              float2 lr = make_float2(0.f, 0.f);
-              if (odd) lr = *reinterpret_cast<const float2*>(io.Lr + e);
-              float2 qn, pn, P;
-              s_leaf_elem(z.x, g0, p.x, sv.x, lr.x, odd, hs, eps_s, qn.x, pn.x, P.x, la);
-              s_leaf_elem(z.y, g1, p.y, sv.y, lr.y, odd, hs, eps_s, qn.y, pn.y, P.y, la);
-              *reinterpret_cast<float2*>(io.qout + e) = qn;
-              *reinterpret_cast<float2*>(io.ph + e) = pn;
-              *reinterpret_cast<float2*>(io.Pdst + e) = P;
-              if (walk) { cz0 += qn.x; cz1 += qn.y; }
-            } else {
-              *reinterpret_cast<float2*>(io.gout + e) = make_float2(g0, g1);
+        const int nrow = min(32, max(0, T - (t0 + 32 * qd)));
+        constexpr int UH = 2;   // days per batch in flight (register budget; the rows were prefetched into L2 at the start of the tile)
+#pragma unroll 1
+        for (int d0 = 0; d0 < nrow; d0 += UH) {
+          float2 zz[UH], pp[UH], ss[UH], ll[UH];
+#pragma unroll
+          for (int u = 0; u < UH; ++u) {
+            const size_t e = e0 + (size_t)(d0 + u) * SP;
+            zz[u] = make_float2(0.f, 0.f); pp[u] = zz[u]; ss[u] = zz[u]; ll[u] = zz[u];
+            if (d0 + u < nrow) {
+              zz[u] = *reinterpret_cast<const float2*>(qin + e);
+              if (LEAF) {
+                pp[u] = *reinterpret_cast<const float2*>(io.ph + e); ss[u] = *reinterpret_cast<const float2*>(io.sm + e);
+                if (odd) ll[u] = *reinterpret_cast<const float2*>(io.Lr + e);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < UH; ++u) {
+            const int d = d0 + u;
+            if (d < nrow) {
+              const int t = t0 + 32 * qd + d;
+              const size_t e = e0 + (size_t)d * SP;
+              const float2 h = *reinterpret_cast<const float2*>(hp + d * pitch);
+              pre.x += h.x; pre.y += h.y;
+              const float2 z = zz[u];
+              qsq = fmaf(z.x, z.x, fmaf(z.y, z.y, qsq));
+              const bool walk = t < T - 1;
+              const float g0 = walk ? fmaf(-m.a_w, pre.x, z.x) : z.x, g1 = walk ? fmaf(-m.a_w, pre.y, z.y) : z.y;
+              if (LEAF) {
+                float2 qn, pn, P;
+                s_leaf_elem(z.x, g0, pp[u].x, ss[u].x, ll[u].x, odd, hs, eps_s, qn.x, pn.x, P.x, la);
+                s_leaf_elem(z.y, g1, pp[u].y, ss[u].y, ll[u].y, odd, hs, eps_s, qn.y, pn.y, P.y, la);
+                *reinterpret_cast<float2*>(io.qout + e) = qn;
+                *reinterpret_cast<float2*>(io.ph + e) = pn;
+                *reinterpret_cast<float2*>(io.Pdst + e) = P;
+                if (walk) { cz0 += qn.x; cz1 += qn.y; }
+              } else {
+                *reinterpret_cast<float2*>(io.gout + e) = make_float2(g0, g1);
+              }
             }
           }
         }

@@ -114,8 +114,7 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
                     full ? (int)d->unadjusted_national[j] : 0, (double)d->n_two_share_national[j], (double)d->n_democrat_national[j], o.xn + j};
   std::stable_sort(hp.begin(), hp.end(), [](const HP& a, const HP& b) { return a.dd != b.dd ? a.dd < b.dd : a.s < b.s; });
   std::vector<uint32_t> pw0(N);
-  std::vector<uint16_t> ppol(N);
-  std::vector<float> pn(N), peh(N), pph(N), prh(N);
+  std::vector<float4> pc(N);
   std::vector<int32_t> tile_ptr(m.NTILE + 1, 0), day_ptr(T + 1, 0);
   double lp_const = 0, cell_max = 1.0, cell_n = 0;
   for (int k = 0; k < N; ++k) {
@@ -125,9 +124,10 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
     float eh = (float)std::log(fc / (1.0 - fc));
     float ph = (float)(1.0 / (1.0 + std::exp(-(double)eh)));
     float rh = (float)(frac - (double)ph);
-    pw0[k] = spack_poll(q.s, q.dd % ST_ROWS, q.mo, q.po, q.un);
-    ppol[k] = (uint16_t)q.p;
-    pn[k] = (float)q.n; peh[k] = eh; pph[k] = ph; prh[k] = rh;
+    const bool head = q.s < S && !(k > 0 && hp[k - 1].dd == q.dd && hp[k - 1].s == q.s);
+    const bool more = k + 1 < N && hp[k + 1].dd == q.dd && hp[k + 1].s == q.s;
+    pw0[k] = spack_poll(q.s, q.dd % ST_ROWS, q.mo, q.po, q.un, q.p, head ? 1 : 0, (head && !more) ? 1 : 0);
+    pc[k] = make_float4((float)q.n, eh, ph, rh);
     double ehd = eh, sp = (ehd > 0 ? ehd : 0) + std::log1p(std::exp(-std::fabs(ehd)));
     lp_const += q.y * ehd - q.n * sp;
     day_ptr[q.dd + 1]++;
@@ -226,11 +226,7 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
   if ((rc = upload_to(al, wv, &p))) return rc; m.w = (const float*)p;
   if ((rc = upload_to(al, lw, &p))) return rc; m.lw = (const float*)p;
   if ((rc = upload_to(al, pw0, &p))) return rc; m.pw0 = (const uint32_t*)p;
-  if ((rc = upload_to(al, ppol, &p))) return rc; m.ppol = (const uint16_t*)p;
-  if ((rc = upload_to(al, pn, &p))) return rc; m.pn = (const float*)p;
-  if ((rc = upload_to(al, peh, &p))) return rc; m.peh = (const float*)p;
-  if ((rc = upload_to(al, pph, &p))) return rc; m.pph = (const float*)p;
-  if ((rc = upload_to(al, prh, &p))) return rc; m.prh = (const float*)p;
+  if ((rc = upload_to(al, pc, &p))) return rc; m.pc = (const float4*)p;
   if ((rc = upload_to(al, tile_ptr, &p))) return rc; m.tile_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, day_ptr, &p))) return rc; m.day_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, perm, &p))) return rc; m.perm = (const uint32_t*)p;

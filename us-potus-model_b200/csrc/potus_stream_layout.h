@@ -17,7 +17,7 @@ constexpr int ST_MAXTILE = ST_MAXT / ST_ROWS;
 constexpr int ST_NZS_CAP = 2048;         // "small" non-walk parameters staged in shared memory: zT, zb, c, m, pop, u_mu, u_rho, ze
 constexpr int ST_NSTAGE = 3;             // B-operand ring (one MMA K-step of 16 per stage)
 constexpr int ST_SEGL = 16;              // residuals per pollster segment (level 1 of the pollster sums)
-constexpr int ST_MAXP = 1024;
+constexpr int ST_MAXP = 512;              // pollster index: 9 bits of the packed poll word
 constexpr int ST_VCHUNK = SNT * 4 * 4;   // vectors are padded to a multiple of this (uniform float4 loops, unrolled by up to 4)
 
 // ---- UMMA operand geometry (K-major, SWIZZLE_NONE, fp16 hi/lo planes).  A: 128 rows x 256 k.
@@ -64,9 +64,11 @@ constexpr int SW_CAND_A = 37, SW_CAND_B = 38;
 constexpr int SW_PCUR = 39, SW_SRUN = 40, SW_G = 41, SW_Q = 42, SW_TMPQ = 43, SW_TMPP = 44;
 constexpr int SW_NSLOT = 45;
 
-// packed poll word: s[0:9) (s == S: national)  day-in-tile[9:16)  mode[16:19)  pop[19:22)  unadjusted[22]
-__host__ __device__ inline uint32_t spack_poll(int s, int dloc, int mo, int po, int un) {
-  return (uint32_t)s | ((uint32_t)dloc << 9) | ((uint32_t)mo << 16) | ((uint32_t)po << 19) | ((uint32_t)un << 22);
+// packed poll word: s[0:9) (s == S: national)  day-in-tile[9:16)  mode[16:18)  pop[18:20)  unadjusted[20]  pollster[21:30)
+//   bit 30: first poll of a (state, day) run of state polls (it writes the run's G cell); bit 31: that run is this poll alone
+__host__ __device__ inline uint32_t spack_poll(int s, int dloc, int mo, int po, int un, int p, int head, int single) {
+  return (uint32_t)s | ((uint32_t)dloc << 9) | ((uint32_t)mo << 16) | ((uint32_t)po << 18) | ((uint32_t)un << 20) | ((uint32_t)p << 21) |
+         ((uint32_t)head << 30) | ((uint32_t)single << 31);
 }
 
 // STREAM LAYOUT of a D-vector (length VL floats, zero in padding):
@@ -92,11 +94,7 @@ struct ModelS {
   const float* w;              // [256]
   const float* lw;             // [256]  L0^T w
   const uint32_t* pw0;         // [N] packed poll word
-  const uint16_t* ppol;        // [N] pollster
-  const float* pn;             // [N] n, eta_hat, p_hat, rho_hat
-  const float* peh;
-  const float* pph;
-  const float* prh;
+  const float4* pc;            // [N] (n, eta_hat, p_hat, rho_hat)
   const int32_t* tile_ptr;     // [NTILE+1] poll range of each tile
   const int32_t* day_ptr;      // [T+1]
   const uint32_t* perm;        // [N] position of sorted poll k in the pollster-grouped residual copy (each pollster padded to ST_SEGL)

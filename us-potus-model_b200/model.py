@@ -112,6 +112,30 @@ class PotusFit:
         d = int(self.stats["n_params"])
         return self._get("inv_metric").reshape((self.cfg.chains, d), order="F")
 
+    def summary(self, ev=None, ev_threshold: float = 270.0, ess: bool = True) -> dict:
+        """On-device post-processing over ALL sampling iterations (potus_postprocess): the election-day state table the
+        reports print (README.Rmd:206-248: mean / sd / quantiles / P(win) per state, national vote), the electoral-college
+        simulation (README.Rmd:271-300) when `ev` is given, and Stan ESS / split R-hat of the monitored scalars."""
+        S = int(self.data["S"])
+        tab = np.zeros((S + 2, 8))
+        et = np.zeros((S + 1, 3)) if ess else None
+        f64p = C.POINTER(C.c_double)
+        evp = None
+        if ev is not None:
+            eva = np.ascontiguousarray(ev, dtype=np.float64)
+            if eva.shape != (S,):
+                raise ValueError("ev must have one entry per state")
+            evp = eva.ctypes.data_as(f64p)
+        cabi.check(self._lib, self._lib.potus_postprocess(self._h, evp, float(ev_threshold), tab.ctypes.data_as(f64p),
+                                                          et.ctypes.data_as(f64p) if ess else None))
+        cols = ("mean", "sd", "q025", "q05", "q50", "q95", "q975", "prob")
+        out = {"states": {c: tab[:S, i].copy() for i, c in enumerate(cols)}, "national": {c: float(tab[S, i]) for i, c in enumerate(cols)}}
+        if ev is not None:
+            out["electoral_votes"] = {c: float(tab[S + 1, i]) for i, c in enumerate(cols)}
+        if ess:
+            out["ess"], out["rhat"], out["monitor_mean"] = et[:, 0].copy(), et[:, 1].copy(), et[:, 2].copy()
+        return out
+
     def save_csvfiles(self, directory: str, basename: str | None = None, chains=None) -> list:
         """cmdstanr `fit$save_output_files()` / `fit$output_files()` analogue: CmdStan-format CSVs that
         rstan::read_stan_csv parses (final_2016.R:543).  See stancsv.py."""
@@ -144,7 +168,7 @@ class CmdStanModelB200:
     def sample(self, data: dict, seed: int = 1843, chains: int = 4, parallel_chains: int | None = None,
                iter_warmup: int = 500, iter_sampling: int = 500, refresh: int | None = None,
                adapt_delta: float = 0.8, max_treedepth: int = 10, keep_per_chain: int = 0, device: int = 0,
-               chain_id_offset: int = 0, init: float = 2.0, force_stream: bool = False, n_gpus: int = 1) -> PotusFit:
+               chain_id_offset: int = 0, init: float = 2.0, force_stream: bool = False, n_gpus: int = 1, state: dict | None = None) -> PotusFit:
         """cmdstanr `$sample()` argument names; `parallel_chains`/`refresh` are accepted and ignored
         (all chains run concurrently on the GPU).  n_gpus > 1: the library itself shards `chains` over that many devices
         in this one process and all-gathers the kept draws with NCCL (include/potus_b200.h, PotusConfig.n_gpus)."""
@@ -162,6 +186,14 @@ class CmdStanModelB200:
         h = C.c_void_p()
         cabi.check(lib, lib.potus_create(C.byref(pd), C.byref(cfg), C.byref(h)))
         try:
+            if state is not None:   # dict(theta=[chains, D], stepsize=[chains], inv_metric=[chains, D]); needs iter_warmup == 0
+                th = np.ascontiguousarray(state["theta"], dtype=np.float64)
+                ep = np.ascontiguousarray(state["stepsize"], dtype=np.float64)
+                im = np.ascontiguousarray(state["inv_metric"], dtype=np.float64)
+                if th.shape != im.shape or th.shape[0] != chains or ep.shape != (chains,):
+                    raise ValueError("state: theta and inv_metric must be [chains, D], stepsize [chains]")
+                f64p = C.POINTER(C.c_double)
+                cabi.check(lib, lib.potus_set_state(h, th.ctypes.data_as(f64p), ep.ctypes.data_as(f64p), im.ctypes.data_as(f64p)))
             cabi.check(lib, lib.potus_run(h))
         except Exception:
             lib.potus_destroy(h)

@@ -1,4 +1,5 @@
-"""Host-side post-processing of the draws, as the reference's reports do it.
+"""Host-side restatement of the reports' post-processing -- the CHECKER of the on-device
+version (csrc/potus_post.cu, `PotusFit.summary()` / `potus_postprocess`), which is what the product path uses.
 
 Restates (numpy, on the election-day slice the sampler's `monitor` buffer holds for EVERY draw):
   README.Rmd:206-220   per-state mean / 2.5% / 97.5% / P(win) of predicted_score[, T, s]
