@@ -115,6 +115,11 @@ typedef struct PotusSampler PotusSampler;
 POTUS_API int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler** out);
 /* Run warm-up + sampling for all chains; blocks until done. */
 POTUS_API int potus_run(PotusSampler* s);
+/* The same in three steps for hosts with an event loop (the R shim polls R_CheckUserInterrupt between polls): begin enqueues all
+ * device work and returns at once, poll sets *done when it has finished, end collects statistics (and runs the all-gather). */
+POTUS_API int potus_run_begin(PotusSampler* s);
+POTUS_API int potus_run_poll(PotusSampler* s, int* done);
+POTUS_API int potus_run_end(PotusSampler* s);
 /* Optional, before potus_run, with iter_warmup == 0: start every chain from a given adapted state (resume / continue a run,
  * or seed the sampling phase from another sampler's warm-up) instead of Stan's random inits + warm-up.
  * theta [chains][D] row-major, Stan unconstrained order; stepsize [chains]; inv_metric [chains][D] (diagonal of M^-1). */

@@ -10,17 +10,24 @@
  * `out` is a named list of REAL arrays with the dims rstan::extract(out, pars)[[1]] has
  * (mu_b [draws,S,T], predicted_score [draws,T,S], ...), see r/potus_b200.R for extract_b200().
  *
- * NOT COMPILED IN THIS IMAGE: R (Rinternals.h, libR) is absent.  Build where R exists:
- *     R CMD SHLIB r/potus_b200_rshim.c -Iinclude -Lus-potus-model_b200/lib -lpotus_b200
+ * NOT COMPILED IN THIS IMAGE: R (Rinternals.h, libR) is absent.  Build where R exists with r/build_rshim.sh
+ * (R CMD SHLIB with -Iinclude and the in-tree libpotus_b200.so on the link line).
  * Contract with R: look names up with R_NamesSymbol, ignore unknown names, accept INTSXP or integral REALSXP
  * for integer fields (R hands `state`, `poll_*`, `n_democrat_*` over as doubles, final_2016.R:436-460),
  * PROTECT every allocation, and call Rf_error() only after every C resource is released (it longjmps).
  */
 #include <R.h>
 #include <Rinternals.h>
+#include <R_ext/Utils.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 #include "potus_b200.h"
+
+/* R_CheckUserInterrupt longjmps; run it under R_ToplevelExec so that the sampler can be destroyed first */
+static void check_interrupt_fn(void* dummy) { (void)dummy; R_CheckUserInterrupt(); }
+static int interrupted(void) { return R_ToplevelExec(check_interrupt_fn, NULL) == FALSE; }
 
 static SEXP list_get(SEXP lst, const char* name) {
   SEXP names = Rf_getAttrib(lst, R_NamesSymbol);
@@ -67,16 +74,21 @@ static SEXP fetch(PotusSampler* s, const char* par, int ndim, const int* dims, i
 
 SEXP potus_nuts_sample(SEXP data, SEXP config) {
   PotusData d; memset(&d, 0, sizeof d);
-  void* owned[32]; int n_owned = 0, ok = 1; R_xlen_t n;
-#define IVEC(field) do { d.field = as_i32(list_get(data, #field), &n, &ok); owned[n_owned++] = (void*)d.field; } while (0)
-#define DVEC(field) do { d.field = as_f64(list_get(data, #field), &n, &ok); owned[n_owned++] = (void*)d.field; } while (0)
+  void* owned[32]; int n_owned = 0, ok = 1, dim_ok = 1; R_xlen_t n; const char* bad_dim = "";
+  /* want < 0: no length check.  A vector shorter than the scalar sizes say would be read past its end by the library:
+   * refuse it here with Stan's own wording ("mismatch in dimension declared and found in context") */
+#define IVEC(field, want) do { d.field = as_i32(list_get(data, #field), &n, &ok); owned[n_owned++] = (void*)d.field; \
+    if (d.field && (want) >= 0 && n != (R_xlen_t)(want)) { dim_ok = 0; bad_dim = #field; } } while (0)
+#define DVEC(field, want) do { d.field = as_f64(list_get(data, #field), &n, &ok); owned[n_owned++] = (void*)d.field; \
+    if (d.field && (want) >= 0 && n != (R_xlen_t)(want)) { dim_ok = 0; bad_dim = #field; } } while (0)
   d.N_national_polls = (int32_t)scalar(data, "N_national_polls", 0); d.N_state_polls = (int32_t)scalar(data, "N_state_polls", 0);
   d.T = (int32_t)scalar(data, "T", 0); d.S = (int32_t)scalar(data, "S", 0); d.P = (int32_t)scalar(data, "P", 0);
   d.M = (int32_t)scalar(data, "M", 1); d.Pop = (int32_t)scalar(data, "Pop", 1);
-  IVEC(state); IVEC(day_state); IVEC(day_national); IVEC(poll_state); IVEC(poll_national);
-  IVEC(poll_mode_state); IVEC(poll_mode_national); IVEC(poll_pop_state); IVEC(poll_pop_national);
-  IVEC(n_democrat_national); IVEC(n_two_share_national); IVEC(n_democrat_state); IVEC(n_two_share_state);
-  DVEC(unadjusted_national); DVEC(unadjusted_state); DVEC(mu_b_prior); DVEC(state_weights); DVEC(state_covariance_0);
+  { const int Ns = d.N_state_polls, Nn = d.N_national_polls, S = d.S;
+  IVEC(state, Ns); IVEC(day_state, Ns); IVEC(day_national, Nn); IVEC(poll_state, Ns); IVEC(poll_national, Nn);
+  IVEC(poll_mode_state, Ns); IVEC(poll_mode_national, Nn); IVEC(poll_pop_state, Ns); IVEC(poll_pop_national, Nn);
+  IVEC(n_democrat_national, Nn); IVEC(n_two_share_national, Nn); IVEC(n_democrat_state, Ns); IVEC(n_two_share_state, Ns);
+  DVEC(unadjusted_national, Nn); DVEC(unadjusted_state, Ns); DVEC(mu_b_prior, S); DVEC(state_weights, S); DVEC(state_covariance_0, S * S); }
   d.sigma_c = scalar(data, "sigma_c", 0); d.sigma_m = scalar(data, "sigma_m", 0); d.sigma_pop = scalar(data, "sigma_pop", 0);
   d.sigma_measure_noise_national = scalar(data, "sigma_measure_noise_national", 0);
   d.sigma_measure_noise_state = scalar(data, "sigma_measure_noise_state", 0); d.sigma_e_bias = scalar(data, "sigma_e_bias", 0);
@@ -94,10 +106,21 @@ SEXP potus_nuts_sample(SEXP data, SEXP config) {
 
   char err[512]; err[0] = 0;
   PotusSampler* s = NULL;
-  int rc = ok ? potus_create(&d, &c, &s) : POTUS_ERR_INVALID_DATA;
+  int rc = (ok && dim_ok) ? potus_create(&d, &c, &s) : POTUS_ERR_INVALID_DATA;
   if (!ok) strncpy(err, "data list: integer fields must hold integers", sizeof err - 1);
-  if (rc == POTUS_OK) rc = potus_run(s);
-  if (rc != POTUS_OK && ok) strncpy(err, potus_last_error(), sizeof err - 1);
+  else if (!dim_ok) snprintf(err, sizeof err, "Exception: mismatch in dimension declared and found in context; processing stage=data initialization; variable name=%s", bad_dim);
+  if (rc == POTUS_OK) {   /* run without blocking R's event loop: poll the device, let the user interrupt */
+    rc = potus_run_begin(s);
+    int done = 0, stop = 0;
+    while (rc == POTUS_OK && !done && !stop) {
+      usleep(100000);
+      rc = potus_run_poll(s, &done);
+      if (!done && interrupted()) stop = 1;
+    }
+    if (stop) { potus_destroy(s); for (int i = 0; i < n_owned; ++i) free(owned[i]); Rf_error("potus_b200: interrupted"); }  /* (destroy waits for the device) */
+    if (rc == POTUS_OK) rc = potus_run_end(s);
+  }
+  if (rc != POTUS_OK && ok && dim_ok) strncpy(err, potus_last_error(), sizeof err - 1);
   SEXP out = R_NilValue;
   int nprot = 0;
   if (rc == POTUS_OK) {
@@ -107,14 +130,44 @@ SEXP potus_nuts_sample(SEXP data, SEXP config) {
     const int dims[][3] = {{nd, d.S, d.T}, {nd, d.P, 0}, {nd, d.M, 0}, {nd, d.Pop, 0}, {nd, d.S, 0}, {nd, d.T, 0}, {nd, d.T, d.S},
                            {c.chains * c.iter_sampling, d.S + 1, 0}, {c.chains * nit, 7, 0}};
     const int nds[] = {3, 2, 2, 2, 2, 2, 3, 2, 2};
-    out = PROTECT(Rf_allocVector(VECSXP, 10)); ++nprot;
-    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 10)); ++nprot;
+    out = PROTECT(Rf_allocVector(VECSXP, 13)); ++nprot;
+    SEXP nm = PROTECT(Rf_allocVector(STRSXP, 13)); ++nprot;
     for (int i = 0; i < 9 && rc == POTUS_OK; ++i) {
       SET_VECTOR_ELT(out, i, fetch(s, names[i], nds[i], dims[i], &rc));
       SET_STRING_ELT(nm, i, Rf_mkChar(names[i]));
     }
     SET_VECTOR_ELT(out, 9, Rf_mkString(d.poll_mode_state ? "poll_model_2020" : "poll_model_2020_no_mode_adjustment"));
     SET_STRING_ELT(nm, 9, Rf_mkChar("model_name"));
+    if (rc == POTUS_OK) {
+      /* chain_id [draws]: global chain of every kept draw (chains are concatenated in chain order) */
+      const int keep = c.chains > 0 ? nd / c.chains : 0;
+      SEXP cid = PROTECT(Rf_allocVector(INTSXP, nd)); ++nprot;
+      for (int r = 0; r < nd; ++r) INTEGER(cid)[r] = c.chain_id_offset + (keep > 0 ? r / keep : 0) + 1;
+      SET_VECTOR_ELT(out, 10, cid); SET_STRING_ELT(nm, 10, Rf_mkChar("chain_id"));
+      /* timing: device seconds (total, warm-up, sampling, all-gather), leapfrogs, launches */
+      SEXP tm = PROTECT(Rf_allocVector(REALSXP, 7)); ++nprot;
+      SEXP tn = PROTECT(Rf_allocVector(STRSXP, 7)); ++nprot;
+      const char* tnames[] = {"seconds_total", "seconds_warmup", "seconds_sampling", "seconds_gather", "n_leapfrog_total", "n_divergent_sampling", "gpu_launches"};
+      const double tv[] = {st.seconds_total, st.seconds_warmup, st.seconds_sampling, st.seconds_gather, (double)st.n_leapfrog_total,
+                           (double)st.n_divergent_sampling, (double)st.gpu_launches};
+      for (int i = 0; i < 7; ++i) { REAL(tm)[i] = tv[i]; SET_STRING_ELT(tn, i, Rf_mkChar(tnames[i])); }
+      Rf_setAttrib(tm, R_NamesSymbol, tn);
+      SET_VECTOR_ELT(out, 11, tm); SET_STRING_ELT(nm, 11, Rf_mkChar("timing"));
+      /* diagnostics [S+1, 3]: Stan ESS, split R-hat, mean of mu_b[,T] (logit) and national_mu_b_average[T], from the
+       * on-device post-processing over every sampling iteration; state_table [S+2, 8] beside it */
+      if (c.n_gpus <= 1 && c.iter_sampling >= 4) {
+        SEXP dg = PROTECT(Rf_allocMatrix(REALSXP, 3, d.S + 1)); ++nprot;      /* filled row-major [S+1][3] = column-major [3, S+1] */
+        SEXP tb = PROTECT(Rf_allocMatrix(REALSXP, 8, d.S + 2)); ++nprot;
+        rc = potus_postprocess(s, NULL, 270.0, REAL(tb), REAL(dg));
+        SEXP both = PROTECT(Rf_allocVector(VECSXP, 2)); ++nprot;
+        SEXP bn = PROTECT(Rf_allocVector(STRSXP, 2)); ++nprot;
+        SET_VECTOR_ELT(both, 0, dg); SET_STRING_ELT(bn, 0, Rf_mkChar("ess_rhat_mean"));
+        SET_VECTOR_ELT(both, 1, tb); SET_STRING_ELT(bn, 1, Rf_mkChar("state_table"));
+        Rf_setAttrib(both, R_NamesSymbol, bn);
+        SET_VECTOR_ELT(out, 12, both);
+      }
+      SET_STRING_ELT(nm, 12, Rf_mkChar("diagnostics"));
+    }
     Rf_setAttrib(out, R_NamesSymbol, nm);
     if (rc != POTUS_OK) strncpy(err, potus_last_error(), sizeof err - 1);
   }

@@ -112,12 +112,12 @@ def test_stream_output_contract_and_sharding(pkg, orc_mod, cuda_lib):
         assert np.abs(c["mu_m"] - ex["mu_m"][k]).max() < 1e-6 and np.abs(c["mu_pop"] - ex["mu_pop"][k]).max() < 1e-6
     mon = fit.monitor()
     assert mon.shape == (4, 4, 65)
-    assert np.allclose(mon[:, 1::2, :64], ex["mu_b"][:, :, 299].reshape(4, 2, 64), atol=1e-6)
+    assert np.allclose(mon[:, 0::2, :64], ex["mu_b"][:, :, 299].reshape(4, 2, 64), atol=1e-6)
     nat = np.einsum("dk,k->d", ex["mu_b"][:, :, 299], d["state_weights"])
-    assert np.allclose(mon[:, 1::2, 64].reshape(-1), nat, atol=2e-5)
+    assert np.allclose(mon[:, 0::2, 64].reshape(-1), nat, atol=2e-5)
     sp = fit.sampler_params()
     lp_o = np.array([om.logp_grad(th[k])[0] for k in range(8)])
-    assert np.abs(sp["lp__"][:, 20:][:, 1::2].reshape(-1) - lp_o).max() < 0.1
+    assert np.abs(sp["lp__"][:, 20:][:, 0::2].reshape(-1) - lp_o).max() < 0.1
     im = fit.inv_metric()
     assert im.shape == (4, om.D) and (im > 0).all()
     a = m.sample(chains=2, chain_id_offset=0, **kw)

@@ -198,8 +198,8 @@ def test_stan_csv_layout_and_roundtrip(pkg, datalists, year, tmp_path):
                 np.testing.assert_allclose(dr["sigma_rho"][k, c], fw["sigma_rho"], atol=1e-9)
                 np.testing.assert_allclose(dr["rho_e_bias"][k, c], fw["rho"], atol=1e-9)
                 np.testing.assert_allclose(dr["mu_e_bias"][k, c], fw["mu_e"], atol=1e-9)
-            # kept iterations are thin*k + thin-1 of the sampling phase
-            it = nw + 4 * k + 3
+            # kept iterations are thin*k of the sampling phase (CmdStan's thin)
+            it = nw + 4 * k
             assert abs(out["sampler_params"]["stepsize__"][k, c] - fit._sp["stepsize__"][c, it]) < 1e-9
         np.testing.assert_allclose(out["inv_metric"][c], fit._im[c], rtol=1e-5)
     # the likelihood through the CSV's own logit_pi columns reproduces the oracle's log density

@@ -17,14 +17,15 @@ nw = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 ns = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 adapted = "adapted" in sys.argv[4:]
 stream = "stream" in sys.argv[4:]
+offset = next((int(a.split("=")[1]) for a in sys.argv[4:] if a.startswith("offset=")), 0)   # global id of the first chain
 data = pkg.load_npz(os.path.join(ROOT, "tests", "golden", "datalist_2016.npz"))
 state = None
 if adapted:
     st = np.load(os.path.join(ROOT, "tests", "golden", "oracle_adapted_states_2016.npz"))
-    idx = np.arange(chains) % st["q"].shape[0]
+    idx = (offset + np.arange(chains)) % st["q"].shape[0]
     state = dict(theta=st["q"][idx].astype(np.float64), stepsize=st["stepsize"][idx], inv_metric=st["inv_metric"][idx].astype(np.float64))
     nw = 0
-fit = pkg.cmdstan_model().sample(data=data, seed=1843, chains=chains, iter_warmup=nw, iter_sampling=ns, keep_per_chain=1, state=state, force_stream=stream)
+fit = pkg.cmdstan_model().sample(data=data, seed=1843, chains=chains, iter_warmup=nw, iter_sampling=ns, keep_per_chain=1, state=state, force_stream=stream, chain_id_offset=offset)
 sp = fit.sampler_params()
 depth, nleap, div = sp["treedepth__"].astype(int), sp["n_leapfrog__"].astype(int), sp["divergent__"].astype(int)
 full = nleap == (2 ** depth - 1)          # every doubling completed: ended at the top level (persist / max depth)

@@ -138,7 +138,7 @@ def make_config(chains=4, iter_warmup=500, iter_sampling=500, seed=1843, keep_pe
 
 _lib = None
 
-EXPORTS = ("potus_create", "potus_run", "potus_set_state", "potus_draws_size", "potus_get_draws", "potus_get_stats",
+EXPORTS = ("potus_create", "potus_run", "potus_run_begin", "potus_run_poll", "potus_run_end", "potus_set_state", "potus_draws_size", "potus_get_draws", "potus_get_stats",
            "potus_device_buffer", "potus_postprocess", "potus_destroy", "potus_last_error", "potus_logp_grad", "potus_logp_grad_ex", "potus_num_params")
 
 
@@ -157,6 +157,12 @@ def load_library(path: str | None = None):
     lib.potus_create.restype = C.c_int
     lib.potus_run.argtypes = [C.c_void_p]
     lib.potus_run.restype = C.c_int
+    lib.potus_run_begin.argtypes = [C.c_void_p]
+    lib.potus_run_begin.restype = C.c_int
+    lib.potus_run_poll.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+    lib.potus_run_poll.restype = C.c_int
+    lib.potus_run_end.argtypes = [C.c_void_p]
+    lib.potus_run_end.restype = C.c_int
     lib.potus_set_state.argtypes = [C.c_void_p, _f64p, _f64p, _f64p]
     lib.potus_set_state.restype = C.c_int
     lib.potus_draws_size.argtypes = [C.c_void_p, C.c_char_p]

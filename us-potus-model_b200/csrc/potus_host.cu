@@ -777,7 +777,6 @@ static int run_multi(PotusSampler* s) {
   NcclApi* nc = nccl_api();
   const int G = (int)s->subs.size();
   int rc;
-  for (PotusSampler* q : s->subs) if ((rc = run_launch(q))) return rc;      // all devices run concurrently
   for (PotusSampler* q : s->subs) if ((rc = run_finish(q))) return rc;
   // the path's one exchange: all-gather of the kept draws over NVLink
   cudaEvent_t g0, g1;
@@ -820,12 +819,39 @@ static int run_multi(PotusSampler* s) {
   return POTUS_OK;
 }
 
-int potus_run(PotusSampler* s) {
+// potus_run in three steps, so that a host with an event loop (R: R_CheckUserInterrupt) is not blocked for the whole run:
+// begin enqueues every launch and returns; poll reports whether the device work has finished; end collects the results
+// (statistics, and with n_gpus > 1 the ncclAllGather).
+int potus_run_begin(PotusSampler* s) {
+  if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
+  int rc;
+  if (!s->subs.empty()) {
+    for (PotusSampler* q : s->subs) if ((rc = run_launch(q))) return rc;      // all devices run concurrently
+    return POTUS_OK;
+  }
+  return run_launch(s);
+}
+int potus_run_poll(PotusSampler* s, int* done) {
+  if (!s || !done) return fail(POTUS_ERR_STATE, "NULL argument");
+  *done = 1;
+  std::vector<PotusSampler*> one{s};
+  for (PotusSampler* q : (s->subs.empty() ? one : s->subs)) {
+    if (!q->ev[2]) return fail(POTUS_ERR_STATE, "potus_run_begin has not been called");
+    CUDA_TRY(cudaSetDevice(q->cfg.device));
+    const cudaError_t e = cudaEventQuery(q->ev[2]);
+    if (e == cudaErrorNotReady) *done = 0;
+    else if (e != cudaSuccess) return fail(POTUS_ERR_CUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(e));
+  }
+  return POTUS_OK;
+}
+int potus_run_end(PotusSampler* s) {
   if (!s) return fail(POTUS_ERR_STATE, "sampler is NULL");
   if (!s->subs.empty()) return run_multi(s);
-  int rc = run_launch(s);
-  if (rc) return rc;
   return run_finish(s);
+}
+int potus_run(PotusSampler* s) {
+  const int rc = potus_run_begin(s);
+  return rc ? rc : potus_run_end(s);
 }
 
 // Start every chain from a given state instead of random inits + warm-up: theta [chains][D] (Stan unconstrained order),

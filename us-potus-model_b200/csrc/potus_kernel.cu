@@ -1443,7 +1443,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
       const int kprev = it - 1 - a.iter_warmup;
       if (kprev >= 0) {
         em.monitor = a.monitor + ((size_t)chain * a.iter_sampling + kprev) * (m.S + 1);
-        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == a.keep_every - 1) {
+        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == 0) {
           const int slot = kprev / a.keep_every;
           if (slot < a.keep_per_chain) em.draw = a.draws + ((size_t)chain * a.keep_per_chain + slot) * a.draw_len;
         }
@@ -1544,7 +1544,7 @@ extern "C" __global__ void __launch_bounds__(NT, 1) potus_nuts_kernel(const __gr
       const int kprev = n_iter_total - 1 - a.iter_warmup;
       if (kprev >= 0) {
         em.monitor = a.monitor + ((size_t)chain * a.iter_sampling + kprev) * (m.S + 1);
-        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == a.keep_every - 1) {
+        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == 0) {
           const int slot = kprev / a.keep_every;
           if (slot < a.keep_per_chain) em.draw = a.draws + ((size_t)chain * a.keep_per_chain + slot) * a.draw_len;
         }

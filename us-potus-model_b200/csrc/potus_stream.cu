@@ -1192,7 +1192,7 @@ extern "C" __global__ void __launch_bounds__(SNT, 1) potus_stream_kernel(const _
       const int kprev = it - 1 - a.iter_warmup;
       if (kprev >= 0) {
         em.monitor = a.monitor + ((size_t)chain * a.iter_sampling + kprev) * (m.S + 1);
-        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == a.keep_every - 1) {
+        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == 0) {
           const int slot = kprev / a.keep_every;
           if (slot < a.keep_per_chain) em.draw = a.draws + ((size_t)chain * a.keep_per_chain + slot) * a.draw_len;
         }
@@ -1278,7 +1278,7 @@ extern "C" __global__ void __launch_bounds__(SNT, 1) potus_stream_kernel(const _
       const int kprev = n_iter_total - 1 - a.iter_warmup;
       if (kprev >= 0) {
         em.monitor = a.monitor + ((size_t)chain * a.iter_sampling + kprev) * (m.S + 1);
-        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == a.keep_every - 1) {
+        if (a.keep_per_chain > 0 && (kprev % a.keep_every) == 0) {
           const int slot = kprev / a.keep_every;
           if (slot < a.keep_per_chain) em.draw = a.draws + ((size_t)chain * a.keep_per_chain + slot) * a.draw_len;
         }

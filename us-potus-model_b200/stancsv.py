@@ -182,7 +182,7 @@ def write_stan_csv(fit, directory: str, basename: str | None = None, chains=None
     theta = fit.theta()
     tp_names = ["mu_b", "mu_c", "polling_bias"] + (["mu_m", "mu_pop", "e_bias"] if _is_full(data) else [])
     tps = fit.extract(tp_names)
-    it_kept = np.arange(keep) * thin + (thin - 1)          # sampling iterations the device kept
+    it_kept = np.arange(keep) * thin                       # sampling iterations the device kept: 0, thin, 2 thin, ... as CmdStan's `thin`
     base = basename or fit.model_name
     el = (float(fit.stats.get("seconds_warmup", 0.0)), float(fit.stats.get("seconds_sampling", 0.0)))
     paths = []
@@ -190,8 +190,10 @@ def write_stan_csv(fit, directory: str, basename: str | None = None, chains=None
         r = slice(c * keep, (c + 1) * keep)
         body = draw_table(data, theta[r], {k: v[r] for k, v in tps.items()})
         diag = np.stack([sp[k][c, it_kept] for k in SAMPLER_COLS], axis=1)
+        if _is_full(data):   # Stan's lp__ carries the constant log-Jacobian log(0.02) of mu_e_bias' multiplier; the library drops constants
+            diag[:, SAMPLER_COLS.index("lp__")] += np.log(0.02)
         note = (f"sampler = potus_b200 (sm_100a resident NUTS, fp32 state); iter_sampling = {int(cfg.iter_sampling)}, "
-                f"kept iterations = {thin}k+{thin - 1}",)
+                f"kept iterations = {thin}k (k = 0, 1, ...)",)
         p = os.path.join(directory, f"{base}-{c + 1}.csv")
         write_chain_csv(p, names, np.concatenate([diag, body], axis=1), model_name=fit.model_name,
                         chain_id=c + 1 + int(getattr(cfg, "chain_id_offset", 0)), seed=int(cfg.seed),
