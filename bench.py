@@ -37,11 +37,11 @@ sys.path.insert(0, ROOT)
 # algo_bytes: SURVEY.md 8(d): read q,p + write q,p once, fp32 state = 4*D*4.  dram_bytes: dram__bytes_read.sum +
 # dram__bytes_write.sum per leapfrog of the kernel from the committed ncu --set full capture named in `ncu`.
 WORKLOADS = {
-    "2016": dict(D=15098, S=51, T=254, N=1619, kernel="potus_nuts_kernel", dram_bytes=25.435008e9 / 286391,
-                 ncu="profiles/r01_e_final_kernel.txt", desc="poll_model_2020.stan, 2016 data list (S=51,T=254,N=1619,D=15098)",
+    "2016": dict(D=15098, S=51, T=254, N=1619, kernel="potus_nuts_kernel", dram_bytes=(3.547104e9 + 6.019785e9) / 75480,
+                 ncu="profiles/r02_resident_sampling_launch.txt: ncu capture of a sampling-phase launch, depth-8 trees", desc="poll_model_2020.stan, 2016 data list (S=51,T=254,N=1619,D=15098)",
                  data="2016 polls (reference data/all_polls.csv through the restated final_2016.R wrangling; committed fixture), random inits"),
-    "syn": dict(D=144837, S=256, T=365, N=50000, kernel="potus_stream_kernel", dram_bytes=None,
-                ncu="profiles/r02_stream_kernel.txt", desc="poll_model_2020.stan, synthetic list of SURVEY.md 8(d) (S=256,T=365,N=40000+10000,P=512,D=144837, seed 1843)",
+    "syn": dict(D=144837, S=256, T=365, N=50000, kernel="potus_stream_kernel", dram_bytes=(846.641933e9 + 415.223650e9) / 150516,
+                ncu="profiles/r02_stream_kernel.txt: ncu capture of a sampling-phase launch, depth-10 trees", desc="poll_model_2020.stan, synthetic list of SURVEY.md 8(d) (S=256,T=365,N=40000+10000,P=512,D=144837, seed 1843)",
                 data="synthetic (generator of SURVEY.md 8(d), numpy PCG64 seed 1843), random inits"),
 }
 

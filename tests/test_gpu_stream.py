@@ -151,3 +151,27 @@ def test_stream_posterior_matches_reference_tables_2016(pkg, datalists, cuda_lib
     z = np.abs(mean - np.array(ora["mean"])) / (4 * np.array(ora["mcse"]) + 5e-4)
     assert z.max() <= 1.0, z.max()
     assert 0.011 < st["mean_stepsize"] < 0.017 and 7.9 < st["mean_treedepth"] < 8.4
+
+
+def test_shapes_the_resident_kernel_refuses_are_routed_to_the_streaming_family(pkg, orc_mod, cuda_lib):
+    """The envelope of the drop-in: whatever Stan's data block allows and the resident kernel cannot hold
+    goes to the streaming family WITHOUT a flag -- fractional `unadjusted_*` (poll_model_2020.stan:22-23: real in [0, 1]),
+    more than 63 polls in one (state, day) cell, T = 300 (BASELINE config 2 says "T~300"), N > 1648 -- and matches the oracle."""
+    rng = np.random.default_rng(8)
+    cases = {}
+    d = small_datalist(S=51, T=254, Ns=300, Nn=50, P=40)
+    d["unadjusted_state"] = rng.uniform(0, 1, 300); d["unadjusted_national"] = rng.uniform(0, 1, 50)
+    cases["fractional unadjusted"] = d
+    cases["100 polls per cell"] = small_datalist(S=2, T=3, Ns=600, Nn=30, P=4)
+    cases["T=300"] = small_datalist(S=51, T=300, Ns=900, Nn=200, P=60)
+    cases["N=4000"] = small_datalist(S=51, T=254, Ns=3200, Nn=800, P=100)
+    for name, d in cases.items():
+        om = orc_mod.OracleModel(d)
+        th = rng.normal(0, 0.5, (2, om.D))
+        lp, g = pkg.logp_grad(d, th)          # no force_stream: potus_create / potus_logp_grad route by themselves
+        for i in range(2):
+            lpo, go = om.logp_grad(th[i])
+            assert abs(lp[i] - lpo) <= 1e-8 * max(abs(lpo), 1e3), (name, lp[i], lpo)
+            assert np.abs(g[i] - go).max() <= 3e-6 * max(np.abs(go).max(), 1.0), (name, np.abs(g[i] - go).max(), np.abs(go).max())
+        fit = pkg.cmdstan_model().sample(data=d, seed=2, chains=2, iter_warmup=6, iter_sampling=2, keep_per_chain=1)
+        assert np.all(np.isfinite(fit.sampler_params()["lp__"])) and fit.extract("mu_b").shape == (2, int(d["S"]), int(d["T"]))

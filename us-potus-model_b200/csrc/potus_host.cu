@@ -606,7 +606,7 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
   // kernel family: the resident kernel when the problem fits it (and config->reserved bit 0 does not force the streaming one)
   const bool want_stream = (config->flags & POTUS_FLAG_FORCE_STREAM) != 0;
   bool use_stream = want_stream;
-  if (!want_stream && check_supported(data) != POTUS_OK) use_stream = true;
+  if (!want_stream && check_supported(data) != POTUS_OK) use_stream = true;   // (size, or fractional unadjusted_*)
   if (use_stream && (rc = check_stream_supported(data))) return rc;
   int n_sm = 0;
   rc = check_device(config->device, &n_sm);
@@ -624,10 +624,21 @@ int potus_create(const PotusData* data, const PotusConfig* config, PotusSampler*
     s->lp_const = ms.lp_const; s->map = &s->sh.map_i2s;
   } else {
     rc = build_model(data, s->hm);
-    if (rc) { potus_destroy(s); return rc; }
-    const ModelDev& mr = s->hm.m;
-    s->S = mr.S; s->T = mr.T; s->P = mr.P; s->M = mr.M; s->Pop = mr.Pop; s->full = mr.full; s->D = mr.D; s->VL = VEC;
-    s->lp_const = mr.lp_const; s->map = &s->hm.map_i2s;
+    if (rc == POTUS_ERR_UNSUPPORTED && check_stream_supported(data) == POTUS_OK) {
+      // a shape detail the resident kernel cannot hold (e.g. more than 63 polls in one (state, day) cell): streaming family
+      free_model(s->hm);
+      s->stream = use_stream = true;
+      rc = build_stream_model(data, s->sh);
+      if (rc) { potus_destroy(s); return rc; }
+      const ModelS& ms = s->sh.m;
+      s->S = ms.S; s->T = ms.T; s->P = ms.P; s->M = ms.M; s->Pop = ms.Pop; s->full = ms.full; s->D = ms.D; s->VL = ms.VL;
+      s->lp_const = ms.lp_const; s->map = &s->sh.map_i2s;
+    } else {
+      if (rc) { potus_destroy(s); return rc; }
+      const ModelDev& mr = s->hm.m;
+      s->S = mr.S; s->T = mr.T; s->P = mr.P; s->M = mr.M; s->Pop = mr.Pop; s->full = mr.full; s->D = mr.D; s->VL = VEC;
+      s->lp_const = mr.lp_const; s->map = &s->hm.map_i2s;
+    }
   }
   const int C = config->chains;
   s->alloc_chains = std::max(C, g_alloc_chains_hint);
@@ -1231,6 +1242,7 @@ int potus_logp_grad_ex(const PotusData* data, const double* theta, int n, double
   if (force_stream || check_supported(data) != POTUS_OK) return logp_grad_stream(data, theta, n, lp, grad);
   HostModel hm;
   rc = build_model(data, hm);
+  if (rc == POTUS_ERR_UNSUPPORTED && check_stream_supported(data) == POTUS_OK) { free_model(hm); return logp_grad_stream(data, theta, n, lp, grad); }
   if (rc) { free_model(hm); return rc; }
   const int D = hm.m.D;
   std::vector<float> qin((size_t)n * VEC, 0.f);

@@ -65,7 +65,8 @@ constexpr uint32_t SM_PRIOR = SM_TOT + NWARP * 52 * 4;      // float [64]
 constexpr uint32_t SM_RED = SM_PRIOR + 64 * 4;              // double [NWARP][12]
 constexpr uint32_t SM_CTL = SM_RED + (NWARP * 12 + 16) * 8; // control block (scalars), 2048 B
 constexpr uint32_t SM_MODEL = SM_CTL + 2048;                // ModelDev copy, 512 B
-constexpr uint32_t SM_TOTAL = SM_MODEL + 512;
+constexpr uint32_t SM_UTAB = SM_MODEL + 512;                // float [256] per-leaf selection uniforms of the current subtree (one Philox per leaf, not per thread)
+constexpr uint32_t SM_TOTAL = SM_UTAB + 1024;
 static_assert(SM_TOTAL + 128 <= 232448, "shared memory budget (227 KiB) exceeded");
 static_assert(255 * SCR_PITCH * 4 <= A_REGION, "scratch must fit in the operand region");
 
@@ -77,7 +78,8 @@ constexpr int SLOT_TOP_BB = 28, SLOT_TOP_FF = 29, SLOT_TOP_RHO = 30;
 constexpr int SLOT_ENDF_Q = 31, SLOT_ENDF_P = 32, SLOT_ENDB_Q = 33, SLOT_ENDB_P = 34;
 constexpr int SLOT_CAND_A = 35, SLOT_CAND_B = 36; // sample / proposal positions (roles swap)
 constexpr int SLOT_TMPQ = 37;
-constexpr int NSLOT = 38;
+constexpr int SLOT_CAND_C = 38;                   // position of the leaf just evaluated (becomes the proposal when it is selected)
+constexpr int NSLOT = 39;
 
 // nz ownership: warp w owns nz slots [192w, 192w+192); inside, lane ln (0..5) owns the float2 pairs (15-d)*6+ln, d = 0..15,
 // so that the six nz lanes of a warp touch 12 consecutive words whenever they walk their elements in step

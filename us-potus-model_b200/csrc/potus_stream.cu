@@ -437,7 +437,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
             float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp] + sigx * x[u];
             if (m.full) {
               eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
-              if ((w0[u] >> 20) & 1) eta += sF(SS_E)[t0 + dl];
+              if ((w0[u] >> 20) & 1) eta = fmaf(m.pun ? __ldg(m.pun + k) : 1.0f, sF(SS_E)[t0 + dl], eta);
             }
             float f, r;
             poll_term(eta, pc[u].x, pc[u].y, pc[u].z, pc[u].w, f, r);
@@ -514,7 +514,7 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
 #pragma unroll
             for (int u = 0; u < 8; ++u) { const int k = kb + 32 * u; w8[u] = 0u; r8[u] = 0.f; if (k < k1) { w8[u] = __ldg(m.pw0 + k); r8[u] = rbuf[k]; } }
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { if ((w8[u] >> 20) & 1) ae += r8[u]; if ((int)(w8[u] & 511) == S) an += r8[u]; }
+            for (int u = 0; u < 8; ++u) { if ((w8[u] >> 20) & 1) ae = fmaf(m.pun ? __ldg(m.pun + kb + 32 * u) : 1.0f, r8[u], ae); if ((int)(w8[u] & 511) == S) an += r8[u]; }
           }
         }
 #pragma unroll

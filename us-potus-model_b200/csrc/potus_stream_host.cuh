@@ -38,13 +38,6 @@ int check_stream_supported(const PotusData* d) {
              "2S+P+M+Pop+2+T<=%d)", d->S, d->T, d->P, d->M, d->Pop, ST_MAXS, ST_MAXT, ST_MAXP, MAX_MODE, ST_NZS_CAP);
     return fail(POTUS_ERR_UNSUPPORTED, buf);
   }
-  if (full)
-    for (int pass = 0; pass < 2; ++pass) {
-      const double* u = pass ? d->unadjusted_national : d->unadjusted_state;
-      int n = pass ? d->N_national_polls : d->N_state_polls;
-      for (int i = 0; i < n; ++i)
-        if (u[i] != 0.0 && u[i] != 1.0) return fail(POTUS_ERR_UNSUPPORTED, "unadjusted_* must be 0 or 1 (fractional values are not supported)");
-    }
   return POTUS_OK;
 }
 
@@ -104,17 +97,22 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
   m.VL = ((m.o_x + N + ST_VCHUNK - 1) / ST_VCHUNK) * ST_VCHUNK;
 
   // ---- polls sorted by (day, state); the national polls of a day (s = S) come last within the day
-  struct HP { int s, dd, p, mo, po, un; double n, y; int stan_x; };
+  struct HP { int s, dd, p, mo, po, un; double n, y; int stan_x; double unf; };   // un: unadjusted != 0; unf: its value in [0, 1]
   std::vector<HP> hp(N);
   for (int i = 0; i < Ns; ++i)
     hp[i] = HP{d->state[i] - 1, d->day_state[i] - 1, d->poll_state[i] - 1, full ? d->poll_mode_state[i] - 1 : 0, full ? d->poll_pop_state[i] - 1 : 0,
-               full ? (int)d->unadjusted_state[i] : 0, (double)d->n_two_share_state[i], (double)d->n_democrat_state[i], o.xs + i};
+               full ? (d->unadjusted_state[i] != 0.0 ? 1 : 0) : 0, (double)d->n_two_share_state[i], (double)d->n_democrat_state[i], o.xs + i,
+               full ? d->unadjusted_state[i] : 0.0};
   for (int j = 0; j < Nn; ++j)
     hp[Ns + j] = HP{S, d->day_national[j] - 1, d->poll_national[j] - 1, full ? d->poll_mode_national[j] - 1 : 0, full ? d->poll_pop_national[j] - 1 : 0,
-                    full ? (int)d->unadjusted_national[j] : 0, (double)d->n_two_share_national[j], (double)d->n_democrat_national[j], o.xn + j};
+                    full ? (d->unadjusted_national[j] != 0.0 ? 1 : 0) : 0, (double)d->n_two_share_national[j], (double)d->n_democrat_national[j], o.xn + j,
+                    full ? d->unadjusted_national[j] : 0.0};
   std::stable_sort(hp.begin(), hp.end(), [](const HP& a, const HP& b) { return a.dd != b.dd ? a.dd < b.dd : a.s < b.s; });
   std::vector<uint32_t> pw0(N);
   std::vector<float4> pc(N);
+  std::vector<float> pun;   // fractional `unadjusted_*` (poll_model_2020.stan:22-23 allows [0, 1]; the reference's lists hold 0 / 1): one weight per poll
+  for (int k = 0; k < N; ++k) if (hp[k].unf != 0.0 && hp[k].unf != 1.0) { pun.assign(N, 0.f); break; }
+  if (!pun.empty()) for (int k = 0; k < N; ++k) pun[k] = (float)hp[k].unf;
   std::vector<int32_t> tile_ptr(m.NTILE + 1, 0), day_ptr(T + 1, 0);
   double lp_const = 0, cell_max = 1.0, cell_n = 0;
   for (int k = 0; k < N; ++k) {
@@ -227,6 +225,8 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
   if ((rc = upload_to(al, lw, &p))) return rc; m.lw = (const float*)p;
   if ((rc = upload_to(al, pw0, &p))) return rc; m.pw0 = (const uint32_t*)p;
   if ((rc = upload_to(al, pc, &p))) return rc; m.pc = (const float4*)p;
+  m.pun = nullptr;
+  if (!pun.empty()) { if ((rc = upload_to(al, pun, &p))) return rc; m.pun = (const float*)p; }
   if ((rc = upload_to(al, tile_ptr, &p))) return rc; m.tile_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, day_ptr, &p))) return rc; m.day_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, perm, &p))) return rc; m.perm = (const uint32_t*)p;

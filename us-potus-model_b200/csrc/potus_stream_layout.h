@@ -95,6 +95,7 @@ struct ModelS {
   const float* lw;             // [256]  L0^T w
   const uint32_t* pw0;         // [N] packed poll word
   const float4* pc;            // [N] (n, eta_hat, p_hat, rho_hat)
+  const float* pun;            // [N] unadjusted weight in [0, 1], or null when every value is 0 / 1 (then bit 20 of the poll word says it all)
   const int32_t* tile_ptr;     // [NTILE+1] poll range of each tile
   const int32_t* day_ptr;      // [T+1]
   const uint32_t* perm;        // [N] position of sorted poll k in the pollster-grouped residual copy (each pollster padded to ST_SEGL)
