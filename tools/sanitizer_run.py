@@ -19,6 +19,10 @@ adapted = "adapted" in sys.argv[4:]
 stream = "stream" in sys.argv[4:]
 offset = next((int(a.split("=")[1]) for a in sys.argv[4:] if a.startswith("offset=")), 0)   # global id of the first chain
 data = pkg.load_npz(os.path.join(ROOT, "tests", "golden", "datalist_2016.npz"))
+if "toy" in sys.argv[4:]:   # a toy list (S=7, T=5, 9 polls, no-mode): short trajectories whose trees often end by the in-subtree U-turn break
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import small_datalist
+    data = small_datalist(S=7, T=5, Ns=9, Nn=0, full=False)
 state = None
 if adapted:
     st = np.load(os.path.join(ROOT, "tests", "golden", "oracle_adapted_states_2016.npz"))

@@ -330,8 +330,6 @@ struct LeafTail {
   const float4* Lr;  // odd leaf: momentum of the previous (even) leaf = Left_0 of the level-0 merge, else null
   float4* Fs;        // even leaf: FIRST[...] slot that receives this leaf's momentum, else null
   float4* Es;        // leaf closing a level-1 left half: its e slot, else null
-  float4* Cs;        // receives the position of THIS leaf (before the position update that is fused in below)
-  float eps_s;       // signed step
   float kk, c1a, c1b;  // out: this thread's partial |P|^2 and the two level-0 U-turn dot products
 };
 
@@ -822,20 +820,6 @@ __device__ __forceinline__ void eval_body(const Emit em, LeafTail& lt) {
           for (int k = 0; k < 2; ++k)   // (its r = b + e is re-formed by the level-1 merge)
             lt.Es[(2 * c + k) * NT] = make_float4(g[4 * k], g[4 * k + 1], g[4 * k + 2], g[4 * k + 3]);
         }
-        // this leaf's position goes to the candidate slot (it becomes the proposal if the multinomial draw selects this leaf)
-        // and the position update q' = q + eps s p_half' happens right here, while p_half' and s are in registers: the
-        // separate pass that re-read both from TMEM is gone.  Safe without a barrier: only the owner touches these elements
-        // until barrier S1 of the next gradient (P5 / P2 cross-thread reads of q are behind barriers S2..S8).
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          float2* qa = qpair(4 * c + 2 * k);
-          float2* qb = qpair(4 * c + 2 * k + 1);
-          float2 a = *qa, b = *qb;
-          lt.Cs[(2 * c + k) * NT] = make_float4(a.x, a.y, b.x, b.y);
-          a.x = fmaf(lt.eps_s * sm[4 * k], p[4 * k], a.x); a.y = fmaf(lt.eps_s * sm[4 * k + 1], p[4 * k + 1], a.y);
-          b.x = fmaf(lt.eps_s * sm[4 * k + 2], p[4 * k + 2], b.x); b.y = fmaf(lt.eps_s * sm[4 * k + 3], p[4 * k + 3], b.y);
-          *qa = a; *qb = b;
-        }
       }
     }
     ptx::tmem_wait_st();
@@ -903,6 +887,25 @@ __device__ __forceinline__ float full_step_momentum(uint32_t tp, float hs) {
   ptx::tmem_wait_st();
   return ss;
 }
+// position update of a leaf: q' = q + eps_signed * s * p_half'   (p_half' was written to TM_P by the fused leaf tail)
+__device__ __forceinline__ void advance_q(uint32_t tp, float eps_signed) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float p[16], s[16];
+    tm_ld16_nowait(tp, TM_P + 16 * h, p);
+    tm_ld16_nowait(tp, TM_S + 16 * h, s);
+    ptx::tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      float2* q = qpair((h * 16 + j) >> 1);
+      float2 v = *q;
+      v.x = fmaf(eps_signed * s[j], p[j], v.x);
+      v.y = fmaf(eps_signed * s[j + 1], p[j + 1], v.y);
+      *q = v;
+    }
+  }
+}
+
 // One U-turn merge (Stan's three criteria) between the completed left subtree L = {b,e,r} and the
 // implicit right subtree R = {b: rb (or P if null), r: P + S, e: P}; S (TM_G) += L.r afterwards.
 // `first` : S is implicitly zero.  (Level 0, where L is a single leaf, is fused into the leaf tail.)
@@ -1035,7 +1038,7 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       }
     }
   }
-  int samp = SLOT_CAND_A, prop = SLOT_CAND_B, cur = SLOT_CAND_C;
+  int samp = SLOT_CAND_A, prop = SLOT_CAND_B;
   if (tid == 0) { ctl.U_samp = U0; ctl.H_samp = H0; ctl.U_prop = U0; ctl.H_prop = H0; ctl.sum_metro = 0.f; }
   float lsw = 0.f;
   int n_leap = 0, depth = 0, loaded = 0;
@@ -1106,8 +1109,6 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       lt.Lr = (t > 0) ? own4((const float*)first_slot(n - 1)) : nullptr;
       lt.Fs = (t == 0 && !last) ? own4(first_slot(n)) : nullptr;
       lt.Es = (t == 1 && !last) ? own4(slot_ptr(ws, SLOT_LEFT) + VEC) : nullptr;
-      lt.Cs = own4(slot_ptr(ws, cur));
-      lt.eps_s = eps_s;
       eval_body<true>(none, lt);
       PROF_RESET;
       // one block reduction for |P|^2 and the two level-0 criteria (its barrier also publishes ctl.U)
@@ -1144,12 +1145,18 @@ __device__ __noinline__ void transition(const RunArgs& a, float* ws, uint32_t ch
       // multinomial selection inside the new subtree (reservoir form of Stan's pairwise rule)
       {
         // (the table entry was written before this leaf's gradient, i.e. behind at least eight barriers)
-        if (n == 0 || SMP(float, SM_UTAB)[n & 255] < __expf(dH - lsw_sub)) {   // the leaf's position is already in slot `cur`: it becomes the proposal
-          const int tmp = prop; prop = cur; cur = tmp;
+        if (n == 0 || SMP(float, SM_UTAB)[n & 255] < __expf(dH - lsw_sub)) {
+          q_to_global(slot_ptr(ws, prop));
           if (tid == 0) { ctl.U_prop = ctl.U; ctl.H_prop = h; }
         }
       }
       PROF(12);
+      // position update q' = q + eps*s*p_half' (after the candidate copy above).  No barrier follows: this is safe only
+      // because, until barrier S1 of the next gradient, every thread reads nothing of q but the elements it owns.
+      // (Fusing this pass into the leaf tail -- writing every leaf's position to a spare candidate slot so that selection
+      //  becomes a pointer swap -- was built and measured in round 2: bit-identical chains, 5 % SLOWER (the eight extra
+      //  128-bit global stores per thread per leaf cost more than the two TMEM re-reads they save); profiles/r02_ab_resident_fusion.log)
+      advance_q(tp, eps_s);
       PROF(15);
       // U-turn checks for every subtree this leaf completes (level 0 came with the reduction above)
       if (t > 0) ok = (c1a > 0.f) && (c1b > 0.f);

@@ -78,8 +78,7 @@ constexpr int SLOT_TOP_BB = 28, SLOT_TOP_FF = 29, SLOT_TOP_RHO = 30;
 constexpr int SLOT_ENDF_Q = 31, SLOT_ENDF_P = 32, SLOT_ENDB_Q = 33, SLOT_ENDB_P = 34;
 constexpr int SLOT_CAND_A = 35, SLOT_CAND_B = 36; // sample / proposal positions (roles swap)
 constexpr int SLOT_TMPQ = 37;
-constexpr int SLOT_CAND_C = 38;                   // position of the leaf just evaluated (becomes the proposal when it is selected)
-constexpr int NSLOT = 39;
+constexpr int NSLOT = 38;
 
 // nz ownership: warp w owns nz slots [192w, 192w+192); inside, lane ln (0..5) owns the float2 pairs (15-d)*6+ln, d = 0..15,
 // so that the six nz lanes of a warp touch 12 consecutive words whenever they walk their elements in step
