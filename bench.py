@@ -301,7 +301,7 @@ def main():
             # iterations, reduced on the device (potus_postprocess) -- the monitor table itself stays on the GPU
             ps = fit.extract("predicted_score"); d2h += ps.size * 4
             sm = fit.summary(ev=data.get("_ev_state"), ess=ns >= 4)
-            d2h += (int(data["S"]) + 2) * 8 * 8 + ((int(data["S"]) + 1) * (n_local * 6 + ((n_local + 7) // 8) * ns) * 8 if ns >= 4 else 0)
+            d2h += (int(data["S"]) + 2) * 8 * 8 + ((int(data["S"]) + 1) * (n_local * 6 + ((n_local + 63) // 64) * ns) * 8 if ns >= 4 else 0)
             d2h += n_local * 72 + 64          # per-chain adaptation state + the device-reduced run statistics (inside potus_run)
             out["summary"] = sm
             out["pred_T"] = ps[:, -1, :]

@@ -949,7 +949,7 @@ int potus_postprocess(PotusSampler* s, const double* ev, double ev_threshold, do
   std::vector<long long> ranks(5);
   std::vector<double> frac(5);
   for (int j = 0; j < 5; ++j) { const double h = (R - 1) * qs[j]; const long long lo = (long long)std::floor(h); ranks[j] = lo + 1; frac[j] = h - lo; }
-  const int cpg = 8, G = (C + cpg - 1) / cpg;
+  const int cpg = 64, G = (C + cpg - 1) / cpg;   // chains per block of the autocovariance kernel (its partial sums are combined on the host)
   float *dsh = nullptr, *dw = nullptr, *dev = nullptr, *dthr = nullptr;
   double *dmom = nullptr, *dsel = nullptr, *dcs = nullptr, *dac = nullptr;
   long long* drank = nullptr;

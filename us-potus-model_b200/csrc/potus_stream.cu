@@ -412,7 +412,10 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       const float* mu = sF(SS_A);
       const float nat_pb = ctl.nat_pb;
       float* rpol = rbuf + m.rp_off;
-      constexpr int UD = 2;   // polls per thread in flight (more costs registers, and spills go to L2: there is almost no L1 left)
+#ifndef POTUS_UD
+#define POTUS_UD 2
+#endif
+      constexpr int UD = POTUS_UD;   // polls per thread in flight (more costs registers, and spills go to L2: there is almost no L1 left)
       for (int kb = p0 + tid; kb < p1; kb += UD * SNT) {
         uint32_t w0[UD], pm[UD];
         float4 pc[UD];
@@ -475,7 +478,10 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     SPROF(5);
     // ---------------- E2: G operand cells = sums of residuals per (state, day); per-day sums for e_bias / national
     {
-      constexpr int UC = 4;
+#ifndef POTUS_UC
+#define POTUS_UC 4
+#endif
+      constexpr int UC = POTUS_UC;
       for (int kb = p0 + tid; kb < p1; kb += UC * SNT) {
         uint32_t wv[UC];
         float rr[UC];
@@ -555,7 +561,10 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
       if (colload) {
         const size_t e0 = (size_t)(t0 + 32 * qd) * SP + c0;
         const int nrow = min(32, max(0, T - (t0 + 32 * qd)));
-        constexpr int UH = 2;   // days per batch in flight (register budget; the rows were prefetched into L2 at the start of the tile)
+#ifndef POTUS_UH
+#define POTUS_UH 2
+#endif
+        constexpr int UH = POTUS_UH;   // days per batch in flight (register budget; the rows were prefetched into L2 at the start of the tile)
 #pragma unroll 1
         for (int d0 = 0; d0 < nrow; d0 += UH) {
           float2 zz[UH], pp[UH], ss[UH], ll[UH];
