@@ -150,7 +150,11 @@ __device__ __forceinline__ void s_gemm(int which, int prefetched) {
   const uint32_t par = c.gemm_cnt & 1;
   if (tid == 32) s_produce(which, prefetched, SMD().KS);
   if (tid == 0) s_issue(which);
-  ptx::mbar_wait(&c.bar_done, par);
+  // (everyone but the issuer and the producer has nothing to do until the accumulators are complete: back off instead of
+  //  spinning, the spin was 4.6 % of all issued instructions and competes with the two working threads for issue slots)
+  while (!ptx::mbar_try_wait(&c.bar_done, par)) {
+    if (tid != 0 && tid != 32) __nanosleep(128);
+  }
   ptx::tc_fence_after();
 }
 __device__ __forceinline__ int s_prefetch(int which) {   // called by ALL threads with a uniform result; thread 32 copies
@@ -478,33 +482,31 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
     SPROF(5);
     // ---------------- E2: G operand cells = sums of residuals per (state, day); per-day sums for e_bias / national
     {
-#ifndef POTUS_UC
-#define POTUS_UC 4
-#endif
-      constexpr int UC = POTUS_UC;
-      for (int kb = p0 + tid; kb < p1; kb += UC * SNT) {
-        uint32_t wv[UC];
-        float rr[UC];
+      {   // one thread per cell descriptor: the run's residuals are contiguous in the sorted residual buffer
+        const int c0 = __ldg(m.tile_cptr + tile), c1 = __ldg(m.tile_cptr + tile + 1);
+        for (int cb = c0 + tid; cb < c1; cb += 2 * SNT) {
+          uint2 cd[2];
+          float acc[2];
 #pragma unroll
-        for (int u = 0; u < UC; ++u) {
-          const int k = kb + u * SNT;
-          wv[u] = 0u; rr[u] = 0.f;
-          if (k < p1) { wv[u] = __ldg(m.pw0 + k); rr[u] = rbuf[k]; }
-        }
+          for (int u = 0; u < 2; ++u) {
+            const int c = cb + u * SNT;
+            cd[u] = make_uint2(0u, 0u); acc[u] = 0.f;
+            if (c < c1) { cd[u] = __ldg(m.cells + c); }
+          }
 #pragma unroll
-        for (int u = 0; u < UC; ++u) {
-          const int k = kb + u * SNT;
-          if ((wv[u] >> 30) & 1) {   // head of a (state, day) run of state polls (bit 31: the run is this poll alone)
-            float acc = rr[u];
-            const uint32_t key = wv[u] & 0xffffu;
-            if (!(wv[u] >> 31))
-              for (int j = k + 1; j < p1 && (__ldg(m.pw0 + j) & 0xffffu) == key; ++j) acc += rbuf[j];
-            const int s = key & 511, dl = key >> 9;
-            __half hi, lo;
-            ptx::split_f16(acc * m.scale_G, hi, lo);
-            const uint32_t o = (uint32_t)(s >> 3) * SA_LBO + (uint32_t)(dl >> 3) * SA_SBO + (uint32_t)(dl & 7) * 16 + (uint32_t)(s & 7) * 2;
-            *reinterpret_cast<__half*>(smem_raw + SS_A + o) = hi;
-            *reinterpret_cast<__half*>(smem_raw + SS_A + SA_PLANE + o) = lo;
+          for (int u = 0; u < 2; ++u) if (cb + u * SNT < c1) acc[u] = rbuf[cd[u].x];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (cb + u * SNT < c1) {
+              const int len = cd[u].y >> 16;
+              for (int j = 1; j < len; ++j) acc[u] += rbuf[cd[u].x + j];
+              const int s = cd[u].y & 511, dl = (cd[u].y >> 9) & 127;
+              __half hi, lo;
+              ptx::split_f16(acc[u] * m.scale_G, hi, lo);
+              const uint32_t o = (uint32_t)(s >> 3) * SA_LBO + (uint32_t)(dl >> 3) * SA_SBO + (uint32_t)(dl & 7) * 16 + (uint32_t)(s & 7) * 2;
+              *reinterpret_cast<__half*>(smem_raw + SS_A + o) = hi;
+              *reinterpret_cast<__half*>(smem_raw + SS_A + SA_PLANE + o) = lo;
+            }
           }
         }
       }

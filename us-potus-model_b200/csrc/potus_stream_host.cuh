@@ -133,6 +133,20 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
     if (k > 0 && hp[k - 1].dd == q.dd && hp[k - 1].s == q.s) cell_n += q.n; else cell_n = q.n;
     if (q.s < S) cell_max = std::max(cell_max, cell_n);
   }
+  // (state, day) runs of state polls: the G operand cells, one descriptor each
+  std::vector<uint2> cells;
+  std::vector<int32_t> tile_cptr(m.NTILE + 1, 0);
+  for (int k = 0; k < N;) {
+    int e = k + 1;
+    while (e < N && hp[e].dd == hp[k].dd && hp[e].s == hp[k].s) ++e;
+    if (hp[k].s < S) {
+      if (e - k > 65535) return fail(POTUS_ERR_UNSUPPORTED, "more than 65535 polls in one (state, day) cell");
+      cells.push_back(make_uint2((uint32_t)k, (uint32_t)hp[k].s | ((uint32_t)(hp[k].dd % ST_ROWS) << 9) | ((uint32_t)(e - k) << 16)));
+      tile_cptr[hp[k].dd / ST_ROWS + 1]++;
+    }
+    k = e;
+  }
+  for (int t = 0; t < m.NTILE; ++t) tile_cptr[t + 1] += tile_cptr[t];
   for (int t = 0; t < T; ++t) day_ptr[t + 1] += day_ptr[t];
   for (int t = 0; t < m.NTILE; ++t) tile_ptr[t + 1] += tile_ptr[t];
   m.lp_const = lp_const;
@@ -229,6 +243,8 @@ int build_stream_model(const PotusData* d, StreamHost& sh) {
   if (!pun.empty()) { if ((rc = upload_to(al, pun, &p))) return rc; m.pun = (const float*)p; }
   if ((rc = upload_to(al, tile_ptr, &p))) return rc; m.tile_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, day_ptr, &p))) return rc; m.day_ptr = (const int32_t*)p;
+  if ((rc = upload_to(al, cells, &p))) return rc; m.cells = (const uint2*)p;
+  if ((rc = upload_to(al, tile_cptr, &p))) return rc; m.tile_cptr = (const int32_t*)p;
   if ((rc = upload_to(al, perm, &p))) return rc; m.perm = (const uint32_t*)p;
   if ((rc = upload_to(al, seg_ptr, &p))) return rc; m.seg_ptr = (const int32_t*)p;
   if ((rc = upload_to(al, sh.map_i2s, &p))) return rc; m.map_i2s = (const int32_t*)p;

@@ -98,6 +98,8 @@ struct ModelS {
   const float* pun;            // [N] unadjusted weight in [0, 1], or null when every value is 0 / 1 (then bit 20 of the poll word says it all)
   const int32_t* tile_ptr;     // [NTILE+1] poll range of each tile
   const int32_t* day_ptr;      // [T+1]
+  const uint2* cells;          // (state, day) runs of state polls in poll order: x = first poll, y = s | day-in-tile << 9 | run length << 16
+  const int32_t* tile_cptr;    // [NTILE+1] cell range of each tile
   const uint32_t* perm;        // [N] position of sorted poll k in the pollster-grouped residual copy (each pollster padded to ST_SEGL)
   const int32_t* seg_ptr;      // [P+1] segment range of each pollster
   const int32_t* map_i2s;      // [VL] vector slot -> Stan unconstrained index (-1 = padding)
