@@ -257,7 +257,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from us_potus_model_b200 import build as _b
-    _b.build()
+    if local_rank == 0:
+        _b.build()                      # (a no-op when the in-tree library is current; only one rank per node ever compiles)
+    if world > 1:
+        dist.barrier()
     model = pkg.cmdstan_model("poll_model_2020.stan")
     total_chains = args.chains * world
     off, n_local = shard_chains(total_chains, world, rank)

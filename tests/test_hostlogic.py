@@ -228,3 +228,23 @@ def test_short_or_long_vectors_are_rejected_before_the_library_sees_them(datalis
     d = dict(base); d["state_covariance_0"] = np.asarray(base["state_covariance_0"])[:50, :50]
     with pytest.raises(ValueError, match="state_covariance_0"):
         cabi.marshal_data(d)
+
+
+def test_reference_arm_line_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm): one JSON line with the same metric/unit,
+    `impl: reference`, both gradient forms of the C restatement timed from the committed adapted oracle states, zero copy
+    bytes.  Runs here, on the host cores (a few seconds)."""
+    import json
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-transitions", "2"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "leapfrog steps/sec" and line["unit"] == "leapfrog/s" and line["higher_is_better"] is True
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value_literal"] > 0 and cb["value_collapsed"] > 0 and cb["value"] == line["value"]
+    assert "adapted oracle states" in cb["sample"] and cb["ess_per_sec_committed_run"]["min"] > 0
+    assert line["e2e"] == {"value": line["value"], "unit": "leapfrog/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["steps"] == 1 and line["config"]["chains"] == cb["cores"]

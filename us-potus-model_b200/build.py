@@ -44,10 +44,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB, os.path.join(CSRC, "potus_lib.cu")]
+    tmp = LIB + f".tmp{os.getpid()}"          # build aside, then rename: a concurrent reader never sees a half-written library
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "potus_lib.cu")]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
+    cmd[cmd.index(tmp)] = LIB
     log = os.path.join(LIB_DIR, "build.log")
     with open(log, "w") as f:
         f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
