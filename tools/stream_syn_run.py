@@ -25,3 +25,10 @@ print("  chain0 eps", np.round(sp["stepsize__"][0], 5).tolist(), flush=True)
 print("  chain0 acc", np.round(sp["accept_stat__"][0], 3).tolist(), flush=True)
 print("  chain0 lp", np.round(sp["lp__"][0], 1).tolist(), "checksum nleap", int(sp["n_leapfrog__"].sum()), "lp", float(sp["lp__"].sum()), flush=True)
 print("  mean depth by iter", np.round(sp["treedepth__"].mean(0), 2).tolist(), flush=True)
+if ns >= 20:
+    sm = fit.summary()
+    print(f"  sampling phase: divergent {st['n_divergent_sampling']}, mean accept {st['mean_accept_stat']:.3f}, mean depth {st['mean_treedepth']:.2f}, mean eps {st['mean_stepsize']:.5f}; "
+          f"ESS of the {len(sm['ess'])} monitored scalars over {chains * ns} draws: min {np.nanmin(sm['ess']):.0f} median {np.nanmedian(sm['ess']):.0f}; split R-hat max {np.nanmax(sm['rhat']):.3f}; "
+          f"min-ESS/s {np.nanmin(sm['ess']) / st['seconds_total']:.1f}", flush=True)
+    print("  eps by iteration (mean over chains, every 10th):", np.round(sp["stepsize__"].mean(0)[::10], 5).tolist(), flush=True)
+    print("  depth by iteration (mean over chains, every 10th):", np.round(sp["treedepth__"].mean(0)[::10], 2).tolist(), flush=True)
