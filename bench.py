@@ -1,20 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: NUTS sampling of poll_model_2020.stan on the 2016 data list.
+"""Benchmark of the hot path: NUTS sampling of poll_model_2020.stan.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --workload syn ...                        BASELINE config 5 on the streaming kernel family
   python bench.py --impl reference ...                      CPU arm (oracle restatement; see below)
 
 Metric (BASELINE.json): leapfrog steps/sec (value) and ESS/sec (extra keys), whole job over N GPUs.
-One STEP = one complete sampler run (Stan-default warm-up + sampling) of `--chains` chains per GPU on
-the 2016 data list (S=51, T=254, 1258+361 polls, D=15098), fresh seed per step; chains are sharded
-over ranks by global chain id (weak scaling: fixed chains per GPU) and the kept draws are exchanged
-with ONE NCCL all-gather inside the timed region.  `value` times potus_run with the data list already
-on the device (CUDA events, max over ranks); `e2e` times the public API end to end from HOST buffers
-(named list in, rstan::extract-shaped arrays out), copies included.
+One STEP = one complete sampler run (warm-up + sampling) of `--chains` chains per GPU, fresh seed per step; chains are
+sharded over ranks by global chain id (weak scaling: fixed chains per GPU) and the kept draws are exchanged with ONE NCCL
+all-gather inside the timed region (its result is used: per-shard checksum in the line).
+  --workload 2016 (default): the 2016 data list (S=51, T=254, 1258+361 polls, D=15098), 1024 chains x (500+500) -- the
+      configuration the metric is quoted on (BASELINE configs 2-4); resident SMEM/TMEM kernel.
+  --workload syn: SURVEY 8(d)'s synthetic S=256 x T=365 x N=50k list (BASELINE config 5), 148 chains x (40+10) per step;
+      streaming kernel family.
+`value` times potus_run with the data list already on the device (CUDA events, max over ranks); `e2e` times the public API
+end to end from HOST buffers: named list in -> extract("predicted_score") of the kept draws (formed on the device, fp32 over
+the bus) + summary() (election-day state table, national vote, electoral-college simulation, ESS / R-hat over EVERY sampling
+iteration, reduced on the device), copies included.
 
-The reference's own implementation of this path is rstan/CmdStan driven from R; neither exists in this
-image (nor can be installed offline), so the CPU arm times the fp64 C restatement in oracle/ on the
-box's host cores and says so (`cpu_baseline.kind = "port"`).  Its hand-coded gradient is far cheaper
+The reference's own implementation of this path is rstan/CmdStan driven from R; neither exists in this image (nor can be
+installed offline: /root/reference is an R project, pip has nothing to install), so the CPU arm times the fp64 C
+restatement in oracle/ on the box's host cores and says so (`cpu_baseline.kind = "port"`): every chain starts from a
+committed adapted oracle state and runs sampling-phase transitions, in the literal per-day mat-vec gradient form (the
+reference's cost model; the reported value) and in the collapsed scan+GEMM form.  Its hand-coded gradient is far cheaper
 than Stan's autodiff tape, so the GPU/CPU ratio understates the ratio against rstan.
 """
 from __future__ import annotations
