@@ -198,33 +198,57 @@ __device__ __forceinline__ void affine_scan(float& A, float& B, int l) {
 //     energy / gradient pair, truncation error < 7e-10 v, ~45 FMAs, no divergence inside a warp;
 //   0.4 <= |d| < 12: the closed form with expm1f / log1pf (warm-up transients);
 //   beyond: direct softplus difference (accuracy irrelevant out there).
-__device__ __forceinline__ void poll_term(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
+// (the series branch alone: branch-free, so that two polls of one thread can be scheduled into each other)
+__device__ __forceinline__ void poll_term_series(float d, float n, float ph, float rh, float& f, float& r) {
+  const float v = ph * (1.0f - ph), w = 1.0f - 2.0f * ph, x2 = d * d;
+  const float e4 = fmaf(-6.0f, v, 1.0f) * (1.0f / 24.0f);
+  const float e6 = fmaf(v, fmaf(120.0f, v, -30.0f), 1.0f) * (1.0f / 720.0f);
+  const float e8 = fmaf(v, fmaf(v, fmaf(-5040.0f, v, 1680.0f), -126.0f), 1.0f) * (1.0f / 40320.0f);
+  const float e10 = fmaf(v, fmaf(v, fmaf(v, fmaf(362880.0f, v, -151200.0f), 17640.0f), -510.0f), 1.0f) * (1.0f / 3628800.0f);
+  const float o5 = fmaf(-12.0f, v, 1.0f) * (1.0f / 120.0f);
+  const float o7 = fmaf(v, fmaf(360.0f, v, -60.0f), 1.0f) * (1.0f / 5040.0f);
+  const float o9 = fmaf(v, fmaf(v, fmaf(-20160.0f, v, 5040.0f), -252.0f), 1.0f) * (1.0f / 362880.0f);
+  const float ev = x2 * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, e10, e8), e6), e4), 0.5f);
+  const float od = x2 * fmaf(x2, fmaf(x2, fmaf(x2, o9, o7), o5), 1.0f / 6.0f);
+  const float g = v * fmaf(w * d, od, ev);
+  const float dev = d * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 10.0f * e10, 8.0f * e8), 6.0f * e6), 4.0f * e4), 1.0f);
+  const float dod = x2 * fmaf(x2, fmaf(x2, fmaf(x2, 9.0f * o9, 7.0f * o7), 5.0f * o5), 0.5f);
+  const float gp = v * fmaf(w, dod, dev);
+  f = n * fmaf(rh, d, -g);
+  r = n * (rh - gp);
+}
+// (|d| >= 0.4: warm-up transients and the far tail)
+__device__ __forceinline__ void poll_term_wide(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
   const float d = eta - eh;
-  const float ad = fabsf(d);
-  if (ad < 0.4f) {
-    const float v = ph * (1.0f - ph), w = 1.0f - 2.0f * ph, x2 = d * d;
-    const float e4 = fmaf(-6.0f, v, 1.0f) * (1.0f / 24.0f);
-    const float e6 = fmaf(v, fmaf(120.0f, v, -30.0f), 1.0f) * (1.0f / 720.0f);
-    const float e8 = fmaf(v, fmaf(v, fmaf(-5040.0f, v, 1680.0f), -126.0f), 1.0f) * (1.0f / 40320.0f);
-    const float e10 = fmaf(v, fmaf(v, fmaf(v, fmaf(362880.0f, v, -151200.0f), 17640.0f), -510.0f), 1.0f) * (1.0f / 3628800.0f);
-    const float o5 = fmaf(-12.0f, v, 1.0f) * (1.0f / 120.0f);
-    const float o7 = fmaf(v, fmaf(360.0f, v, -60.0f), 1.0f) * (1.0f / 5040.0f);
-    const float o9 = fmaf(v, fmaf(v, fmaf(-20160.0f, v, 5040.0f), -252.0f), 1.0f) * (1.0f / 362880.0f);
-    const float ev = x2 * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, e10, e8), e6), e4), 0.5f);
-    const float od = x2 * fmaf(x2, fmaf(x2, fmaf(x2, o9, o7), o5), 1.0f / 6.0f);
-    const float g = v * fmaf(w * d, od, ev);
-    const float dev = d * fmaf(x2, fmaf(x2, fmaf(x2, fmaf(x2, 10.0f * e10, 8.0f * e8), 6.0f * e6), 4.0f * e4), 1.0f);
-    const float dod = x2 * fmaf(x2, fmaf(x2, fmaf(x2, 9.0f * o9, 7.0f * o7), 5.0f * o5), 0.5f);
-    const float gp = v * fmaf(w, dod, dev);
-    f = n * fmaf(rh, d, -g);
-    r = n * (rh - gp);
-  } else if (ad < 12.0f) {
+  if (fabsf(d) < 12.0f) {
     // ll(eta) - ll(eta_hat) = n [ (y/n) d - log1p(p_hat expm1(d)) ]
     const float em1 = expm1f(d);
     const float uu = ph * em1;
     f = n * (rh * d + (ph * d - log1pf(uu)));
     r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
   } else {  // far tail: direct, stable softplus difference
+    const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
+    const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
+    const float sg = 1.0f / (1.0f + __expf(-eta));
+    f = n * ((ph + rh) * d - (sp - sph));
+    r = n * ((ph + rh) - sg);
+  }
+}
+// (out-of-line copy for callers that want the common path to stay one basic block)
+__device__ __noinline__ void poll_term_wide_cold(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
+  poll_term_wide(eta, n, eh, ph, rh, f, r);
+}
+__device__ __forceinline__ void poll_term(float eta, float n, float eh, float ph, float rh, float& f, float& r) {
+  const float d = eta - eh;
+  const float ad = fabsf(d);
+  if (ad < 0.4f) {
+    poll_term_series(d, n, ph, rh, f, r);
+  } else if (ad < 12.0f) {
+    const float em1 = expm1f(d);
+    const float uu = ph * em1;
+    f = n * (rh * d + (ph * d - log1pf(uu)));
+    r = n * (rh - ph * (1.0f - ph) * __fdividef(em1, 1.0f + uu));
+  } else {
     const float sp = fmaxf(eta, 0.f) + log1pf(__expf(-fabsf(eta)));
     const float sph = fmaxf(eh, 0.f) + log1pf(__expf(-fabsf(eh)));
     const float sg = 1.0f / (1.0f + __expf(-eta));

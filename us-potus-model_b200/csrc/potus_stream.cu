@@ -420,54 +420,92 @@ __device__ __forceinline__ void s_sweep_body(SweepIO& io, float* rbuf) {
 #define POTUS_UD 2
 #endif
       constexpr int UD = POTUS_UD;   // polls per thread in flight (more costs registers, and spills go to L2: there is almost no L1 left)
-      for (int kb = p0 + tid; kb < p1; kb += UD * SNT) {
-        uint32_t w0[UD], pm[UD];
-        float4 pc[UD];
-        float x[UD], pv[UD], sv[UD], lrv[UD];
-#pragma unroll
-        for (int u = 0; u < UD; ++u) {
-          const int k = kb + u * SNT;
-          if (k < p1) {
-            w0[u] = __ldg(m.pw0 + k); pm[u] = __ldg(m.perm + k);
-            pc[u] = __ldg(m.pc + k);
-            x[u] = qin[m.o_x + k];
-            if (LEAF) { const size_t e = (size_t)m.o_x + k; pv[u] = io.ph[e]; sv[u] = io.sm[e]; lrv[u] = odd ? io.Lr[e] : 0.f; }
-          }
+      static_assert(UD == 2, "the branch-free main loop below is written for two polls per thread");
+      const float fullf = m.full ? 1.0f : 0.f;
+      int kb = p0 + tid;
+      // main part: both polls of the batch exist.  One basic block for the common case (no bounds tests, selects instead of
+      // branches, the series branch of the poll term for both polls) so that the two polls' dependency chains can be
+      // scheduled into each other; polls outside the series' range are redone by the wide form afterwards (rare once a
+      // chain is near its typical set)
+      for (; kb + SNT < p1; kb += 2 * SNT) {
+        const int k0 = kb, k1 = kb + SNT;
+        const uint32_t wa = __ldg(m.pw0 + k0), wb = __ldg(m.pw0 + k1), pma = __ldg(m.perm + k0), pmb = __ldg(m.perm + k1);
+        const float4 pca = __ldg(m.pc + k0), pcb = __ldg(m.pc + k1);
+        const size_t ea = (size_t)m.o_x + k0, eb = (size_t)m.o_x + k1;
+        const float xa = qin[ea], xb = qin[eb];
+        float pva = 0.f, pvb = 0.f, sva = 0.f, svb = 0.f, lra = 0.f, lrb = 0.f;
+        if (LEAF) { pva = io.ph[ea]; pvb = io.ph[eb]; sva = io.sm[ea]; svb = io.sm[eb]; if (odd) { lra = io.Lr[ea]; lrb = io.Lr[eb]; } }
+        const float una = ((wa >> 20) & 1) ? (m.pun ? __ldg(m.pun + k0) : 1.0f) : 0.f, unb = ((wb >> 20) & 1) ? (m.pun ? __ldg(m.pun + k1) : 1.0f) : 0.f;
+        const int sa = wa & 511, sb = wb & 511, dla = (wa >> 9) & 127, dlb = (wb >> 9) & 127;
+        const int moa = (wa >> 16) & 3, mob = (wb >> 16) & 3, poa = (wa >> 18) & 3, pob = (wb >> 18) & 3;
+        const bool nata = (sa == S), natb = (sb == S);
+        const float sga = nata ? m.sig_n : m.sig_s, sgb = natb ? m.sig_n : m.sig_s;
+        // (national polls: mu[dl][S] and PB[S] are valid shared-memory addresses whose values the select discards)
+        float etaa = (nata ? sF(SS_NAT)[dla] + nat_pb : mu[dla * pitch + sa] + sF(SS_PB)[sa]) + m.sig_c * qnz[(m.o_c - oz) + ((wa >> 21) & 511)] + sga * xa;
+        float etab = (natb ? sF(SS_NAT)[dlb] + nat_pb : mu[dlb * pitch + sb] + sF(SS_PB)[sb]) + m.sig_c * qnz[(m.o_c - oz) + ((wb >> 21) & 511)] + sgb * xb;
+        etaa += fullf * (m.sig_m * qnz[(m.o_m - oz) + moa] + m.sig_pop * qnz[(m.o_pop - oz) + poa]);
+        etab += fullf * (m.sig_m * qnz[(m.o_m - oz) + mob] + m.sig_pop * qnz[(m.o_pop - oz) + pob]);
+        etaa = fmaf(una, sF(SS_E)[t0 + dla], etaa);
+        etab = fmaf(unb, sF(SS_E)[t0 + dlb], etab);
+        const float da = etaa - pca.y, db = etab - pcb.y;
+        float fa, ra, fb, rb;
+        poll_term_series(da, pca.x, pca.z, pca.w, fa, ra);
+        poll_term_series(db, pcb.x, pcb.z, pcb.w, fb, rb);
+        if (!(fabsf(da) < 0.4f)) poll_term_wide_cold(etaa, pca.x, pca.y, pca.z, pca.w, fa, ra);
+        if (!(fabsf(db) < 0.4f)) poll_term_wide_cold(etab, pcb.x, pcb.y, pcb.z, pcb.w, fb, rb);
+        fsum += fa; fsum += fb;
+        rbuf[k0] = ra; rbuf[k1] = rb;
+        rpol[pma] = ra; rpol[pmb] = rb;
+        qsq = fmaf(xa, xa, qsq); qsq = fmaf(xb, xb, qsq);
+        const float gxa = xa - sga * ra, gxb = xb - sgb * rb;
+        if (LEAF) {
+          float qn, pn, P;
+          s_leaf_elem(xa, gxa, pva, sva, lra, odd, hs, eps_s, qn, pn, P, la);
+          io.qout[ea] = qn; io.ph[ea] = pn; io.Pdst[ea] = P;
+          s_leaf_elem(xb, gxb, pvb, svb, lrb, odd, hs, eps_s, qn, pn, P, la);
+          io.qout[eb] = qn; io.ph[eb] = pn; io.Pdst[eb] = P;
+        } else {
+          io.gout[ea] = gxa; io.gout[eb] = gxb;
         }
 #pragma unroll
-        for (int u = 0; u < UD; ++u) {
-          const int k = kb + u * SNT;
-          if (k < p1) {
-            const int s = w0[u] & 511, dl = (w0[u] >> 9) & 127, mo = (w0[u] >> 16) & 3, po = (w0[u] >> 18) & 3, pp = (w0[u] >> 21) & 511;
-            const bool nat = (s == S);
-            const float sigx = nat ? m.sig_n : m.sig_s;
-            float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp] + sigx * x[u];
-            if (m.full) {
-              eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
-              if ((w0[u] >> 20) & 1) eta = fmaf(m.pun ? __ldg(m.pun + k) : 1.0f, sF(SS_E)[t0 + dl], eta);
-            }
-            float f, r;
-            poll_term(eta, pc[u].x, pc[u].y, pc[u].z, pc[u].w, f, r);
-            fsum += f;
-            rbuf[k] = r;
-            rpol[pm[u]] = r;
-            qsq = fmaf(x[u], x[u], qsq);
-            const float gx = x[u] - sigx * r;
-            if (LEAF) {
-              const size_t e = (size_t)m.o_x + k;
-              float qn, pn, P;
-              s_leaf_elem(x[u], gx, pv[u], sv[u], lrv[u], odd, hs, eps_s, qn, pn, P, la);
-              io.qout[e] = qn; io.ph[e] = pn; io.Pdst[e] = P;
-            } else {
-              io.gout[(size_t)m.o_x + k] = gx;
-            }
-            if (m.full) {
-#pragma unroll
-              for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
-              gm[MAX_MODE - 1] += r;
-            }
-          }
+        for (int j = 0; j < MAX_MODE - 1; ++j) {
+          gm[j] += (moa == j) ? ra : 0.f; gp[j] += (poa == j) ? ra : 0.f;
+          gm[j] += (mob == j) ? rb : 0.f; gp[j] += (pob == j) ? rb : 0.f;
         }
+        gm[MAX_MODE - 1] += ra; gm[MAX_MODE - 1] += rb;
+      }
+      // tail: at most one poll of this thread is left
+      if (kb < p1) {
+        const int k = kb;
+        const uint32_t w0 = __ldg(m.pw0 + k), pm = __ldg(m.perm + k);
+        const float4 pc = __ldg(m.pc + k);
+        const size_t e = (size_t)m.o_x + k;
+        const float x = qin[e];
+        const int s = w0 & 511, dl = (w0 >> 9) & 127, mo = (w0 >> 16) & 3, po = (w0 >> 18) & 3, pp = (w0 >> 21) & 511;
+        const bool nat = (s == S);
+        const float sigx = nat ? m.sig_n : m.sig_s;
+        float eta = (nat ? sF(SS_NAT)[dl] + nat_pb : mu[dl * pitch + s] + sF(SS_PB)[s]) + m.sig_c * qnz[(m.o_c - oz) + pp] + sigx * x;
+        if (m.full) {
+          eta += m.sig_m * qnz[(m.o_m - oz) + mo] + m.sig_pop * qnz[(m.o_pop - oz) + po];
+          if ((w0 >> 20) & 1) eta = fmaf(m.pun ? __ldg(m.pun + k) : 1.0f, sF(SS_E)[t0 + dl], eta);
+        }
+        float f, r;
+        poll_term(eta, pc.x, pc.y, pc.z, pc.w, f, r);
+        fsum += f;
+        rbuf[k] = r;
+        rpol[pm] = r;
+        qsq = fmaf(x, x, qsq);
+        const float gx = x - sigx * r;
+        if (LEAF) {
+          float qn, pn, P;
+          s_leaf_elem(x, gx, io.ph[e], io.sm[e], odd ? io.Lr[e] : 0.f, odd, hs, eps_s, qn, pn, P, la);
+          io.qout[e] = qn; io.ph[e] = pn; io.Pdst[e] = P;
+        } else {
+          io.gout[e] = gx;
+        }
+#pragma unroll
+        for (int j = 0; j < MAX_MODE - 1; ++j) { gm[j] += (mo == j) ? r : 0.f; gp[j] += (po == j) ? r : 0.f; }
+        gm[MAX_MODE - 1] += r;
       }
     }
     SPROF(4);
