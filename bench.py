@@ -231,7 +231,7 @@ def main():
     ap.add_argument("--iter-sampling", type=int, default=None, help="default 500 (2016) / 10 (syn)")
     ap.add_argument("--keep-per-chain", type=int, default=3, help="full draws kept per chain (1024x3 ~ the reference's 6x500)")
     ap.add_argument("--seed", type=int, default=1843)
-    ap.add_argument("--cpu-iters", type=int, default=3, help="syn workload: bounded CPU sample, iterations per chain")
+    ap.add_argument("--cpu-iters", type=int, default=8, help="syn workload: bounded CPU sample, iterations per chain")
     ap.add_argument("--cpu-transitions", type=int, default=10, help="2016 workload: sampling-phase transitions per chain of the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--warmup-scale", type=float, default=0.1,
