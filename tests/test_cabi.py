@@ -92,3 +92,24 @@ def test_invalid_data_is_rejected_like_stan(cuda_lib, datalists):
     assert rc == -2 and "outside the streaming kernel" in msg
     big = __import__("potus_pkg").load().synthetic_datalist(S=60, T=600, N_state=500, N_national=100, P=20)
     assert create(big)[0] == -2
+
+
+def test_hot_kernels_are_tcgen05_and_bulk_copy_code(cuda_lib):
+    """The product kernels must be the sm_100a code the design describes, not a recompiled mma.sync / cp.async path: every
+    sampler / evaluation kernel holds tcgen05 MMAs (SASS UTCHMMA), TMEM loads (LDTM), tcgen05.commit (UTCBAR) and 1-D bulk
+    async copies (UBLKCP); nothing in the library uses the warp-level HMMA pipe.  (B200_PROFILING.md: PTX -> SASS names.)"""
+    import shutil
+    import subprocess
+    from us_potus_model_b200 import build as b
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", b.LIB], capture_output=True, text=True, check=True).stdout
+    parts = re.split(r"\n\s*Function : (\w+)\n", sass)
+    fun = {parts[i]: parts[i + 1] for i in range(1, len(parts) - 1, 2)}
+    for k in ("potus_nuts_kernel", "potus_eval_kernel", "potus_stream_kernel", "potus_stream_eval_kernel"):
+        assert k in fun, sorted(fun)
+        for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP"):
+            assert re.search(rf"\b{mnemonic}\b", fun[k]), (k, mnemonic)
+    assert "arch = sm_100a" in sass
+    assert not re.search(r"\bHMMA\.", sass) and "LDGSTS" not in sass
