@@ -6,7 +6,6 @@ import numpy as np
 import pytest
 
 from conftest import small_datalist
-import potus_oracle as po
 
 
 @pytest.fixture(scope="module")
